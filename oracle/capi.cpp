@@ -1,0 +1,171 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see field.hpp header).  PARITY UNPINNED BY STORED FIXTURES.
+// C entry points for tests/ (ctypes), __graft_entry__.smoke() and bench.py's cpu_baseline leg.
+// All field elements cross this boundary as u32 Montgomery words (the reference's in-memory form).
+#include "basefold.hpp"
+#include <cstdio>
+#include <cstdlib>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+static inline const F* asF(const uint32_t* p) { return reinterpret_cast<const F*>(p); }
+static inline F* asF(uint32_t* p) { return reinterpret_cast<F*>(p); }
+
+static void put(std::vector<uint32_t>& o, F x) { o.push_back(x.v); }
+static void put(std::vector<uint32_t>& o, const EF& x) { for (int i = 0; i < 4; i++) o.push_back(x.c[i].v); }
+static void put(std::vector<uint32_t>& o, const Digest& d) { for (int i = 0; i < 8; i++) o.push_back(d.d[i].v); }
+static void put(std::vector<uint32_t>& o, const OpeningAndProof& op) {
+    for (F v : op.values) put(o, v);
+    put(o, op.proof.merkle_root);
+    o.push_back(op.proof.log_tensor_height);
+    o.push_back((uint32_t)op.proof.width);
+    for (auto& d : op.proof.paths) put(o, d);
+}
+// flat word order = field order of slop_basefold::BasefoldProof (slop/crates/basefold/src/verifier.rs:97-116)
+static void put(std::vector<uint32_t>& o, const BasefoldProof& p) {
+    for (auto& m : p.univariate_messages) { put(o, m[0]); put(o, m[1]); }
+    for (auto& d : p.fri_commitments) put(o, d);
+    for (auto& c : p.component) put(o, c);
+    for (auto& c : p.query_phase) put(o, c);
+    put(o, p.final_poly);
+    put(o, p.pow_witness);
+    put(o, p.batch_grinding_witness);
+}
+static void put(std::vector<uint32_t>& o, const StackedProof& p) {
+    put(o, p.basefold);
+    for (auto& r : p.batch_evaluations) for (auto& e : r) put(o, e);
+}
+
+static void chal_load(Challenger& c, const uint32_t* s) {
+    for (int i = 0; i < 16; i++) c.sponge[i].v = s[i];
+    for (int i = 0; i < 8; i++) c.inbuf[i].v = s[16 + i];
+    for (int i = 0; i < 8; i++) c.outbuf[i].v = s[24 + i];
+    c.nin = (int)s[32]; c.nout = (int)s[33];
+}
+static void chal_store(const Challenger& c, uint32_t* s) {
+    for (int i = 0; i < 16; i++) s[i] = c.sponge[i].v;
+    for (int i = 0; i < 8; i++) s[16 + i] = c.inbuf[i].v;
+    for (int i = 0; i < 8; i++) s[24 + i] = c.outbuf[i].v;
+    s[32] = (uint32_t)c.nin; s[33] = (uint32_t)c.nout;
+}
+
+extern "C" {
+
+int orc_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// ---- field -------------------------------------------------------------------------------------
+uint32_t orc_to_monty(uint32_t canonical) { return F::from_canonical(canonical).v; }
+uint32_t orc_from_monty(uint32_t m) { return F::raw(m).canonical(); }
+uint32_t orc_mul(uint32_t a, uint32_t b) { return (F::raw(a) * F::raw(b)).v; }
+uint32_t orc_add(uint32_t a, uint32_t b) { return (F::raw(a) + F::raw(b)).v; }
+uint32_t orc_sub(uint32_t a, uint32_t b) { return (F::raw(a) - F::raw(b)).v; }
+uint32_t orc_inv(uint32_t a) { return F::raw(a).inv().v; }
+uint32_t orc_two_adic_generator(uint32_t k) { return two_adic_generator(k).v; }
+void orc_ext_mul(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    EF r = EF::from_base_slice(asF(a)) * EF::from_base_slice(asF(b));
+    for (int i = 0; i < 4; i++) out[i] = r.c[i].v;
+}
+void orc_ext_inv(const uint32_t* a, uint32_t* out) {
+    EF r = EF::from_base_slice(asF(a)).inv();
+    for (int i = 0; i < 4; i++) out[i] = r.c[i].v;
+}
+
+// ---- poseidon2 ---------------------------------------------------------------------------------
+void orc_poseidon2_permute(uint32_t* state16) { poseidon2_permute(asF(state16)); }
+void orc_hash(const uint32_t* in, uint64_t n, uint32_t* out8) {
+    Digest d = p2_hash(asF(in), n);
+    for (int i = 0; i < 8; i++) out8[i] = d.d[i].v;
+}
+void orc_compress(const uint32_t* l, const uint32_t* r, uint32_t* out8) {
+    Digest a, b;
+    for (int i = 0; i < 8; i++) { a.d[i].v = l[i]; b.d[i].v = r[i]; }
+    Digest d = p2_compress(a, b);
+    for (int i = 0; i < 8; i++) out8[i] = d.d[i].v;
+}
+
+// ---- challenger (state = 34 words: sponge[16] input[8] output[8] n_in n_out) --------------------
+void orc_challenger_init(uint32_t* st) { Challenger c; chal_store(c, st); }
+void orc_challenger_observe(uint32_t* st, const uint32_t* vals, uint64_t n) {
+    Challenger c; chal_load(c, st); c.observe_slice(asF(vals), n); chal_store(c, st);
+}
+void orc_challenger_sample(uint32_t* st, uint32_t* out, uint64_t n) {
+    Challenger c; chal_load(c, st); for (uint64_t i = 0; i < n; i++) out[i] = c.sample().v; chal_store(c, st);
+}
+uint32_t orc_challenger_sample_bits(uint32_t* st, uint32_t bits) {
+    Challenger c; chal_load(c, st); uint32_t r = c.sample_bits(bits); chal_store(c, st); return r;
+}
+uint32_t orc_challenger_grind(uint32_t* st, uint32_t bits) {
+    Challenger c; chal_load(c, st); F w = c.grind(bits); chal_store(c, st); return w.v;
+}
+int orc_challenger_check_witness(uint32_t* st, uint32_t bits, uint32_t w) {
+    Challenger c; chal_load(c, st); bool ok = c.check_witness(bits, F::raw(w)); chal_store(c, st); return ok;
+}
+
+// ---- RS encode / Merkle ------------------------------------------------------------------------
+void orc_rs_encode(const uint32_t* msg, uint64_t ncols, uint32_t log_h, uint32_t log_blowup, uint32_t* out) {
+    rs_encode_columns(asF(msg), ncols, log_h, log_blowup, asF(out));
+}
+void orc_dft_naive(const uint32_t* msg, uint64_t msg_len, uint32_t log_n, uint32_t* out) {
+    dft_bitrev_naive(asF(msg), msg_len, asF(out), log_n);
+}
+// layers_out (optional): all digests bottom-up, layer k at offset sum_{j<k} 2^(log_h-j) digests
+void orc_merkle_commit(const uint32_t* mat_colmajor, uint64_t width, uint32_t log_h, uint32_t* layers_out,
+                       uint32_t* root8, uint32_t* commit8) {
+    MerkleTree t = merkle_commit_columns(asF(mat_colmajor), width, log_h);
+    for (int i = 0; i < 8; i++) { root8[i] = t.root.d[i].v; commit8[i] = t.commitment.d[i].v; }
+    if (layers_out) {
+        size_t off = 0;
+        for (auto& L : t.layers) for (auto& d : L) { for (int i = 0; i < 8; i++) layers_out[off + i] = d.d[i].v; off += 8; }
+    }
+}
+
+// ---- stacked PCS + BaseFold: commit rounds, prove at a point, verify with the restated verifier -----
+// dense[r]: column-major [ncols[r] x 2^log_h] for each of n_rounds rounds.  point: (n_extra + log_h) EF
+// elements as 4 words each (only the last log_h are used by BaseFold).  challenger_state: in/out.
+// proof_out: flat words (see put(BasefoldProof)); returns number of words, or -1 if the restated verifier
+// rejects the oracle's own proof.  commits_out: n_rounds x 8 words.
+int64_t orc_stacked_prove_verify(const uint32_t* const* dense, const uint64_t* ncols, uint32_t n_rounds, uint32_t log_h,
+                                 const uint32_t* point, uint32_t point_len, uint32_t log_blowup, uint32_t num_queries,
+                                 uint32_t pow_bits, uint32_t batch_pow_bits, const uint32_t* replay_witnesses,
+                                 uint32_t* challenger_state, uint32_t* commits_out, uint32_t* proof_out,
+                                 uint64_t proof_cap) {
+    FriParams fp; fp.log_blowup = log_blowup; fp.num_queries = num_queries; fp.pow_bits = pow_bits; fp.batch_pow_bits = batch_pow_bits;
+    std::vector<std::shared_ptr<StackedRound>> rounds;
+    std::vector<Digest> commits;
+    std::vector<size_t> areas;
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        rounds.push_back(stacked_commit(asF(dense[r]), ncols[r], log_h, fp));
+        commits.push_back(rounds.back()->tree.commitment);
+        areas.push_back(ncols[r] << log_h);
+        for (int i = 0; i < 8; i++) commits_out[r * 8 + i] = commits.back().d[i].v;
+    }
+    std::vector<EF> pt(point_len);
+    for (uint32_t i = 0; i < point_len; i++) pt[i] = EF::from_base_slice(asF(point + 4 * i));
+    Challenger ch; chal_load(ch, challenger_state);
+    Challenger vch = ch;
+    F rw[2];
+    if (replay_witnesses) { rw[0] = F::raw(replay_witnesses[0]); rw[1] = F::raw(replay_witnesses[1]); }
+    StackedProof sp = stacked_prove(pt, rounds, ch, fp, replay_witnesses ? rw : nullptr);
+    chal_store(ch, challenger_state);
+    // evaluation claim of the stacked polynomial at the full point
+    std::vector<EF> flat;
+    for (auto& r : sp.batch_evaluations) flat.insert(flat.end(), r.begin(), r.end());
+    std::vector<EF> batch_point(pt.begin(), pt.end() - log_h);
+    EF claim = mle_eval(flat.data(), flat.size(), batch_point);
+    const char* err = stacked_verify(commits, areas, pt, sp, claim, vch, log_h, fp);
+    if (err) { std::fprintf(stderr, "oracle verifier rejected oracle proof: %s\n", err); return -1; }
+    std::vector<uint32_t> o;
+    put(o, sp);
+    if (proof_out) { if (o.size() > proof_cap) return -2; std::copy(o.begin(), o.end(), proof_out); }
+    return (int64_t)o.size();
+}
+
+}  // extern "C"

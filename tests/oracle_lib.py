@@ -1,0 +1,170 @@
+"""ctypes binding of oracle/liboracle.so — the CPU checker.  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+P = 0x7F000001
+
+u32p = C.POINTER(C.c_uint32)
+
+
+def _build():
+    if not os.path.exists(_SO):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _build()
+        L = C.CDLL(_SO)
+        L.orc_num_threads.restype = C.c_int
+        for n in ("orc_to_monty", "orc_from_monty", "orc_inv", "orc_two_adic_generator"):
+            getattr(L, n).restype = C.c_uint32
+            getattr(L, n).argtypes = [C.c_uint32]
+        for n in ("orc_mul", "orc_add", "orc_sub"):
+            getattr(L, n).restype = C.c_uint32
+            getattr(L, n).argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_challenger_sample_bits.restype = C.c_uint32
+        L.orc_challenger_grind.restype = C.c_uint32
+        L.orc_challenger_check_witness.restype = C.c_int
+        L.orc_stacked_prove_verify.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def ptr(a):
+    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u32p)
+
+
+def to_monty(x):
+    """canonical -> Montgomery, vectorised in numpy"""
+    x = np.asarray(x, dtype=np.uint64)
+    return ((x << np.uint64(32)) % np.uint64(P)).astype(np.uint32)
+
+
+def from_monty(x):
+    x = np.asarray(x, dtype=np.uint64)
+    # x * 2^-32 mod p ; 2^-32 mod p computed with python ints
+    rinv = pow(1 << 32, P - 2, P)
+    return ((x * np.uint64(rinv)) % np.uint64(P)).astype(np.uint32)
+
+
+def rand_field(rng, shape):
+    """uniform canonical field elements, returned as Montgomery words"""
+    return to_monty(rng.integers(0, P, size=shape, dtype=np.uint64))
+
+
+def permute(state):
+    s = np.ascontiguousarray(state, dtype=np.uint32).copy()
+    lib().orc_poseidon2_permute(ptr(s))
+    return s
+
+
+def hash_(vals):
+    v = np.ascontiguousarray(vals, dtype=np.uint32)
+    out = np.zeros(8, dtype=np.uint32)
+    lib().orc_hash(ptr(v), C.c_uint64(v.size), ptr(out))
+    return out
+
+
+def compress(l, r):
+    l = np.ascontiguousarray(l, dtype=np.uint32)
+    r = np.ascontiguousarray(r, dtype=np.uint32)
+    out = np.zeros(8, dtype=np.uint32)
+    lib().orc_compress(ptr(l), ptr(r), ptr(out))
+    return out
+
+
+def rs_encode(msg, log_blowup):
+    """msg: [ncols, 2^log_h] uint32 (each column contiguous) -> [ncols, 2^(log_h+log_blowup)]"""
+    msg = np.ascontiguousarray(msg, dtype=np.uint32)
+    ncols, h = msg.shape
+    log_h = h.bit_length() - 1
+    assert 1 << log_h == h
+    out = np.zeros((ncols, h << log_blowup), dtype=np.uint32)
+    lib().orc_rs_encode(ptr(msg), C.c_uint64(ncols), C.c_uint32(log_h), C.c_uint32(log_blowup), ptr(out))
+    return out
+
+
+def dft_naive(msg, log_n):
+    msg = np.ascontiguousarray(msg, dtype=np.uint32)
+    out = np.zeros(1 << log_n, dtype=np.uint32)
+    lib().orc_dft_naive(ptr(msg), C.c_uint64(msg.size), C.c_uint32(log_n), ptr(out))
+    return out
+
+
+def merkle_commit(mat, want_layers=False):
+    """mat: [width, 2^log_h] (each column contiguous).  -> (root, commitment[, layers flat [2^(log_h+1)-1, 8]])"""
+    mat = np.ascontiguousarray(mat, dtype=np.uint32)
+    width, h = mat.shape
+    log_h = h.bit_length() - 1
+    root = np.zeros(8, dtype=np.uint32)
+    commit = np.zeros(8, dtype=np.uint32)
+    layers = np.zeros((2 * h - 1, 8), dtype=np.uint32) if want_layers else None
+    lib().orc_merkle_commit(ptr(mat), C.c_uint64(width), C.c_uint32(log_h),
+                            ptr(layers) if want_layers else None, ptr(root), ptr(commit))
+    return (root, commit, layers) if want_layers else (root, commit)
+
+
+class Challenger:
+    def __init__(self, state=None):
+        self.st = np.zeros(34, dtype=np.uint32)
+        if state is None:
+            lib().orc_challenger_init(ptr(self.st))
+        else:
+            self.st[:] = state
+
+    def clone(self):
+        return Challenger(self.st.copy())
+
+    def observe(self, vals):
+        v = np.ascontiguousarray(np.atleast_1d(vals), dtype=np.uint32)
+        lib().orc_challenger_observe(ptr(self.st), ptr(v), C.c_uint64(v.size))
+
+    def sample(self, n=1):
+        out = np.zeros(n, dtype=np.uint32)
+        lib().orc_challenger_sample(ptr(self.st), ptr(out), C.c_uint64(n))
+        return out
+
+    def sample_bits(self, bits):
+        return int(lib().orc_challenger_sample_bits(ptr(self.st), C.c_uint32(bits)))
+
+    def grind(self, bits):
+        return int(lib().orc_challenger_grind(ptr(self.st), C.c_uint32(bits)))
+
+    def check_witness(self, bits, w):
+        return bool(lib().orc_challenger_check_witness(ptr(self.st), C.c_uint32(bits), C.c_uint32(w)))
+
+
+def stacked_prove_verify(dense_rounds, log_h, point, challenger, log_blowup=2, num_queries=124, pow_bits=16,
+                         batch_pow_bits=5, replay=None):
+    """dense_rounds: list of [ncols, 2^log_h] arrays.  point: [k,4] uint32 with k >= log_h.
+    Returns (commits [n_rounds,8], proof words) — raises if the restated verifier rejects."""
+    rounds = [np.ascontiguousarray(d, dtype=np.uint32) for d in dense_rounds]
+    n = len(rounds)
+    arr = (u32p * n)(*[ptr(r) for r in rounds])
+    ncols = (C.c_uint64 * n)(*[r.shape[0] for r in rounds])
+    point = np.ascontiguousarray(point, dtype=np.uint32)
+    commits = np.zeros((n, 8), dtype=np.uint32)
+    cap = 1 << 24
+    proof = np.zeros(cap, dtype=np.uint32)
+    rw = None
+    if replay is not None:
+        rw = np.ascontiguousarray(replay, dtype=np.uint32)
+    nwords = lib().orc_stacked_prove_verify(arr, ncols, C.c_uint32(n), C.c_uint32(log_h), ptr(point),
+                                            C.c_uint32(point.shape[0]), C.c_uint32(log_blowup), C.c_uint32(num_queries),
+                                            C.c_uint32(pow_bits), C.c_uint32(batch_pow_bits),
+                                            ptr(rw) if rw is not None else None, ptr(challenger.st), ptr(commits),
+                                            ptr(proof), C.c_uint64(cap))
+    if nwords < 0:
+        raise RuntimeError(f"oracle stacked_prove_verify failed ({nwords})")
+    return commits, proof[:nwords].copy()

@@ -1,0 +1,212 @@
+"""CPU tests pinning the oracle: reference constant tables, field identities, naive DFT, Merkle/verifier round trips."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+
+P = O.P
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_field_constants_and_roots_match_reference_tables():
+    g = json.load(open(os.path.join(GOLD, "ref_constants.json")))
+    L = O.lib()
+    assert g["p"] == P
+    # sppark/ntt/parameters/koala_bear.h forward_roots_of_unity (Montgomery words)
+    for k, w in enumerate(g["two_adic_roots_monty"]):
+        assert L.orc_two_adic_generator(k) == w, k
+    for k, w in enumerate(g["two_adic_inv_roots_monty"]):
+        assert L.orc_inv(L.orc_two_adic_generator(k)) == w, k
+    # kb31_t.cuh:76-85
+    assert L.orc_to_monty(1) == 0x01FFFFFE
+    assert L.orc_mul(0x17F7EFE4, 1) == 0x01FFFFFE  # RR * 1 (raw) -> R
+
+
+def test_field_ops_against_python_ints():
+    rng = np.random.default_rng(1)
+    L = O.lib()
+    a = rng.integers(0, P, 200)
+    b = rng.integers(0, P, 200)
+    for x, y in zip(a.tolist(), b.tolist()):
+        mx, my = L.orc_to_monty(x), L.orc_to_monty(y)
+        assert L.orc_from_monty(L.orc_mul(mx, my)) == x * y % P
+        assert L.orc_from_monty(L.orc_add(mx, my)) == (x + y) % P
+        assert L.orc_from_monty(L.orc_sub(mx, my)) == (x - y) % P
+        if x:
+            assert L.orc_from_monty(L.orc_inv(mx)) == pow(x, P - 2, P)
+    assert (O.from_monty(O.to_monty(a)) == a).all()
+
+
+def _ext_mul_py(a, b):
+    t = [0] * 7
+    for i in range(4):
+        for j in range(4):
+            t[i + j] += a[i] * b[j]
+    return [(t[0] + 3 * t[4]) % P, (t[1] + 3 * t[5]) % P, (t[2] + 3 * t[6]) % P, t[3] % P]
+
+
+def test_ext_mul_inv():
+    rng = np.random.default_rng(2)
+    L = O.lib()
+    for _ in range(50):
+        a = rng.integers(0, P, 4)
+        b = rng.integers(0, P, 4)
+        ma, mb = O.to_monty(a), O.to_monty(b)
+        out = np.zeros(4, dtype=np.uint32)
+        L.orc_ext_mul(O.ptr(ma), O.ptr(mb), O.ptr(out))
+        assert O.from_monty(out).tolist() == _ext_mul_py(a.tolist(), b.tolist())
+        inv = np.zeros(4, dtype=np.uint32)
+        L.orc_ext_inv(O.ptr(ma), O.ptr(inv))
+        L.orc_ext_mul(O.ptr(ma), O.ptr(inv), O.ptr(out))
+        assert O.from_monty(out).tolist() == [1, 0, 0, 0]
+
+
+def _poseidon2_py(state):
+    """independent python-int statement of the permutation (canonical domain) from SURVEY.md A.2:
+    internal matrix = 2^-32 * (J + diag(-2,1,2,...,2^13,2^15))."""
+    g = json.load(open(os.path.join(GOLD, "ref_constants.json")))
+    ext, inr = g["rc_external_canonical"], g["rc_internal_canonical"]
+    rinv = pow(1 << 32, P - 2, P)
+    diag = [P - 2] + [1 << k for k in range(14)] + [1 << 15]
+    M4 = [[2, 3, 1, 1], [1, 2, 3, 1], [1, 1, 2, 3], [3, 1, 1, 2]]
+
+    def ext_layer(s):
+        t = []
+        for q in range(4):
+            x = s[4 * q:4 * q + 4]
+            t += [sum(M4[i][j] * x[j] for j in range(4)) % P for i in range(4)]
+        sums = [sum(t[4 * q + j] for q in range(4)) % P for j in range(4)]
+        return [(t[i] + sums[i % 4]) % P for i in range(16)]
+
+    def int_layer(s):
+        tot = sum(s) % P
+        return [(tot + diag[i] * s[i]) * rinv % P for i in range(16)]
+
+    s = ext_layer(list(state))
+    for r in range(4):
+        s = ext_layer([pow((s[i] + ext[r][i]) % P, 3, P) for i in range(16)])
+    for r in range(20):
+        s[0] = pow((s[0] + inr[r]) % P, 3, P)
+        s = int_layer(s)
+    for r in range(4, 8):
+        s = ext_layer([pow((s[i] + ext[r][i]) % P, 3, P) for i in range(16)])
+    return s
+
+
+def test_poseidon2_matches_python_statement():
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        s = rng.integers(0, P, 16)
+        out = O.from_monty(O.permute(O.to_monty(s)))
+        assert out.tolist() == _poseidon2_py(s.tolist())
+    # zero state too
+    assert O.from_monty(O.permute(np.zeros(16, np.uint32))).tolist() == _poseidon2_py([0] * 16)
+
+
+def test_sponge_and_compress_semantics():
+    rng = np.random.default_rng(4)
+    for n in (1, 7, 8, 9, 16, 24, 91):
+        v = O.rand_field(rng, n)
+        st = np.zeros(16, np.uint32)
+        for i in range(0, n, 8):
+            chunk = v[i:i + 8]
+            st[:len(chunk)] = chunk  # overwrite mode
+            st = O.permute(st)
+        assert (O.hash_(v) == st[:8]).all()
+    l, r = O.rand_field(rng, 8), O.rand_field(rng, 8)
+    assert (O.compress(l, r) == O.permute(np.concatenate([l, r]))[:8]).all()
+
+
+def test_challenger_semantics():
+    rng = np.random.default_rng(5)
+    c = O.Challenger()
+    v = O.rand_field(rng, 11)
+    c.observe(v)
+    # 8 absorbed -> one duplex; 3 pending; sample duplexes again and pops from the back
+    st = np.zeros(16, np.uint32)
+    st[:8] = v[:8]
+    st = O.permute(st)
+    st[:3] = v[8:]
+    st = O.permute(st)
+    s = c.sample(3)
+    assert s.tolist() == [st[7], st[6], st[5]]
+    # observe clears the output buffer
+    c.observe(v[:1])
+    st[:1] = v[:1]
+    st = O.permute(st)
+    assert c.sample(1)[0] == st[7]
+    # grind: canonical-min witness is valid and leaves the challenger in the post-check state
+    c2 = c.clone()
+    w = c.grind(8)
+    assert c2.check_witness(8, w)
+    assert (c2.st == c.st).all()
+    for smaller in range(O.lib().orc_from_monty(w)):
+        c3 = O.Challenger(c2.st)  # state is post-witness; re-derive from a fresh clone instead
+    # minimality
+    base = O.Challenger()
+    base.observe(v)
+    base.sample(3)
+    base.observe(v[:1])
+    base.sample(1)
+    wc = O.lib().orc_from_monty(w)
+    for cand in range(wc):
+        assert not base.clone().check_witness(8, O.lib().orc_to_monty(cand))
+
+
+@pytest.mark.parametrize("log_h,log_blowup", [(0, 2), (1, 2), (3, 2), (5, 1), (6, 2)])
+def test_rs_encode_matches_naive_dft(log_h, log_blowup):
+    rng = np.random.default_rng(6)
+    msg = O.rand_field(rng, (3, 1 << log_h))
+    cw = O.rs_encode(msg, log_blowup)
+    for c in range(3):
+        assert (cw[c] == O.dft_naive(msg[c], log_h + log_blowup)).all()
+
+
+def test_rs_encode_linearity_large():
+    rng = np.random.default_rng(7)
+    a = O.rand_field(rng, (1, 1 << 12))
+    b = O.rand_field(rng, (1, 1 << 12))
+    s = ((a.astype(np.uint64) + b) % P).astype(np.uint32)
+    ca, cb, cs = O.rs_encode(a, 2), O.rs_encode(b, 2), O.rs_encode(s, 2)
+    assert (((ca.astype(np.uint64) + cb) % P).astype(np.uint32) == cs).all()
+
+
+def test_merkle_layers_and_commitment():
+    rng = np.random.default_rng(8)
+    mat = O.rand_field(rng, (11, 16))
+    root, commit, layers = O.merkle_commit(mat, want_layers=True)
+    for i in range(16):
+        assert (layers[i] == O.hash_(mat[:, i])).all()
+    off, n = 0, 16
+    while n > 1:
+        for i in range(n // 2):
+            assert (layers[off + n + i] == O.compress(layers[off + 2 * i], layers[off + 2 * i + 1])).all()
+        off += n
+        n //= 2
+    assert (layers[-1] == root).all()
+    meta = O.to_monty(np.array([4, 11]))
+    assert (commit == O.compress(root, O.hash_(meta))).all()
+
+
+@pytest.mark.parametrize("ncols,log_h", [([3], 4), ([2, 5], 5), ([1], 1)])
+def test_stacked_basefold_roundtrip(ncols, log_h):
+    """prover -> restated verifier accepts; replaying the witnesses reproduces the identical proof"""
+    rng = np.random.default_rng(9)
+    rounds = [O.rand_field(rng, (c, 1 << log_h)) for c in ncols]
+    extra = max(1, int(np.ceil(np.log2(sum(ncols)))))
+    point = O.rand_field(rng, (extra + log_h, 4))
+    ch = O.Challenger()
+    ch.observe(O.rand_field(rng, 5))
+    ch1 = ch.clone()
+    commits, proof = O.stacked_prove_verify(rounds, log_h, point, ch1, num_queries=10, pow_bits=6, batch_pow_bits=3)
+    assert proof.size > 0
+    # witnesses are the last two words of the basefold part; find them by re-running in replay mode
+    nevals = sum(ncols) * 4
+    pow_w, batch_w = proof[-nevals - 2], proof[-nevals - 1]
+    ch2 = ch.clone()
+    commits2, proof2 = O.stacked_prove_verify(rounds, log_h, point, ch2, num_queries=10, pow_bits=6, batch_pow_bits=3,
+                                              replay=[batch_w, pow_w])
+    assert (proof == proof2).all() and (commits == commits2).all() and (ch1.st == ch2.st).all()

@@ -1,0 +1,130 @@
+/* sp1b200.h — C ABI of the B200-native SP1 (Hypercube, v6) core-shard prover hot path.
+ *
+ * This is the drop-in boundary: a Rust shim implementing `sp1_hypercube::prover::AirProver`
+ * (reference: crates/hypercube/src/prover/shard.rs:45-101), selected through
+ * `SP1ProverComponents::CoreProver` (crates/prover/src/components.rs:148-198), binds these symbols the way
+ * sp1-gpu's own FFI binds its kernels (sp1-gpu/crates/sys/src/runtime.rs:5-20,151-158).  See INTEGRATION.md.
+ *
+ * Conventions (mirroring the reference FFI):
+ *  - every fallible call returns NULL on success or a NUL-terminated message owned by the library
+ *    (valid until the next call on the same thread)            [CudaRustError, sys/src/runtime.rs:5-20]
+ *  - field elements are u32 KoalaBear Montgomery words (R = 2^32), byte-compatible with p3's KoalaBear;
+ *    extension elements are 4 consecutive words; digests are 8 words   [kb31_t.cuh:76-85, kb31_extension_t.cuh:6-63]
+ *  - matrices are column-major: column c occupies [c*height, (c+1)*height)      [sp1-gpu/crates/utils/src/traces.rs:48-75]
+ *  - pointers named `*_any` may be host or device pointers (resolved with cudaPointerGetAttributes);
+ *    `d_*` must be device pointers, `h_*` host pointers
+ *  - all work is enqueued on the context's stream; calls that return data to the host synchronise it
+ *  - the Fiat-Shamir challenger crosses the boundary as 34 words: sponge[16] input[8] output[8] n_in n_out
+ *    (same struct the reference ships to the device, sys/include/challenger/challenger.cuh:13-60)
+ */
+#ifndef SP1B200_H
+#define SP1B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sp1b200_ctx sp1b200_ctx;
+typedef const char* sp1b200_err; /* NULL == ok */
+
+/* protocol parameters: crates/prover/src/components.rs:16-17, crates/primitives/src/fri_params.rs:5-58,
+ * slop/crates/basefold/src/verifier.rs:16, crates/hypercube/src/verifier/shard.rs:41 */
+typedef struct sp1b200_params {
+    uint32_t log_stacking_height; /* 21 */
+    uint32_t max_log_row_count;   /* 22 */
+    uint32_t log_blowup;          /* 2  */
+    uint32_t num_queries;         /* 124 */
+    uint32_t pow_bits;            /* 16 */
+    uint32_t batch_pow_bits;      /* 5  */
+    uint32_t gkr_pow_bits;        /* 12 */
+    uint32_t grind_mode;          /* 0 = canonical-min witness (deterministic), 1 = replay supplied witnesses */
+} sp1b200_params;
+
+#define SP1B200_CHALLENGER_WORDS 34
+#define SP1B200_DIGEST_WORDS 8
+
+/* ---- context / runtime (replaces sp1-gpu/crates/cuda TaskScope + sys/lib/runtime/*.cu) ---------------- */
+sp1b200_err sp1b200_ctx_create(int device, const sp1b200_params* params, sp1b200_ctx** out);
+void sp1b200_ctx_destroy(sp1b200_ctx* ctx);
+sp1b200_err sp1b200_ctx_sync(sp1b200_ctx* ctx);
+void sp1b200_default_core_params(sp1b200_params* out);
+const char* sp1b200_version(void);
+/* raw cudaStream_t of the context (so a host runtime can order its own copies against it) */
+void* sp1b200_ctx_stream(sp1b200_ctx* ctx);
+/* stream-ordered device memory (replaces cuda_malloc_async / cuda_free_async, sys/lib/runtime/memory.cu) */
+sp1b200_err sp1b200_malloc(sp1b200_ctx* ctx, size_t bytes, void** d_out);
+sp1b200_err sp1b200_free(sp1b200_ctx* ctx, void* d_ptr);
+sp1b200_err sp1b200_memcpy_h2d(sp1b200_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+sp1b200_err sp1b200_memcpy_d2h(sp1b200_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
+uint64_t sp1b200_launch_count(sp1b200_ctx* ctx);
+/* device time in ms of the most recent call of the named phase ("rs_encode", "leaf_hash", "compress", ...),
+ * measured with CUDA events on the context stream; -1 if unknown */
+float sp1b200_last_phase_ms(sp1b200_ctx* ctx, const char* phase);
+
+/* ---- kernel-level entry points (replace the per-kernel FFI of sp1-gpu/crates/sys/src/*.rs) ------------- */
+
+/* Poseidon2 permutation of n independent 16-word states (poseidon2.cuh:46-80). */
+sp1b200_err sp1b200_poseidon2_permute(sp1b200_ctx* ctx, uint32_t* states_any, uint64_t n);
+
+/* Reed-Solomon encode: per column zero-pad x 2^log_blowup, forward DFT, rows bit-reversed
+ * (replaces batch_coset_dft, sys/include/ntt/sppark.cuh:49-107; semantics slop/crates/dft/src/p3.rs:11-48).
+ * msg: [ncols x 2^log_h], out: [ncols x 2^(log_h+log_blowup)], both column-major. */
+sp1b200_err sp1b200_rs_encode(sp1b200_ctx* ctx, const uint32_t* msg_any, uint64_t ncols, uint32_t log_h,
+                              uint32_t log_blowup, uint32_t* out_any);
+
+/* Merkle tensor commitment of a column-major [width x 2^log_h] matrix: leaf i = sponge(row i), binary
+ * compress layers, commitment = compress(root, hash([log_h, width]))
+ * (replaces leafHashPacked/compress, sys/lib/merkle_tree/merkle_tree.cu:27-94; semantics
+ * slop/crates/merkle-tree/src/p3sync.rs:40-143).  d_layers_out (optional, device): all 2^(log_h+1)-1 digests,
+ * bottom-up (layer k of 2^(log_h-k) digests after layers 0..k-1).  root/commit: 8 words each, host. */
+sp1b200_err sp1b200_merkle_commit(sp1b200_ctx* ctx, const uint32_t* mat_any, uint64_t width, uint32_t log_h,
+                                  uint32_t* d_layers_out, uint32_t* h_root8, uint32_t* h_commit8);
+
+/* Proof-of-work grind on a challenger state (replaces grindKernel, sys/include/challenger/challenger.cuh:114-158;
+ * semantics p3 DuplexChallenger::grind).  Returns the MINIMUM canonical witness (deterministic) and leaves
+ * `state` in the post-check_witness state (sp1-gpu/crates/challenger/src/grinding_challenger.rs:70-74). */
+sp1b200_err sp1b200_grind(sp1b200_ctx* ctx, uint32_t* h_state34, uint32_t bits, uint32_t* h_witness);
+
+/* Host-side transcript helpers on the 34-word state (no device work; semantics challenger.cuh:22-112,
+ * slop/crates/challenger/src/lib.rs:54-82).  Provided so a shim can keep its challenger in this format. */
+void sp1b200_challenger_init(uint32_t* h_state34);
+void sp1b200_challenger_observe(uint32_t* h_state34, const uint32_t* h_vals, uint64_t n);
+void sp1b200_challenger_sample(uint32_t* h_state34, uint32_t* h_out, uint64_t n);
+uint32_t sp1b200_challenger_sample_bits(uint32_t* h_state34, uint32_t bits);
+int sp1b200_challenger_check_witness(uint32_t* h_state34, uint32_t bits, uint32_t witness);
+
+/* ---- PCS-level entry points (replace sp1-gpu/crates/{commit,basefold}) -------------------------------- */
+
+typedef struct sp1b200_commit sp1b200_commit; /* device-resident prover data of one commitment round */
+
+/* Stacked-PCS commit of a dense buffer already laid out as [ncols x 2^log_stacking_height] column-major
+ * (zero padding applied by the caller or by sp1b200_jagged_commit): RS-encode + Merkle commit
+ * (slop/crates/stacked/src/prover.rs:59-94 -> basefold-prover/src/prover.rs:78-99).
+ * keep_codeword != 0 keeps the 2^log_blowup x larger codeword resident for the query phase; otherwise it is
+ * recomputed on demand (the reference's drop_ldes, sp1-gpu/crates/basefold/src/fri.rs:333-359). */
+sp1b200_err sp1b200_stacked_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, uint64_t ncols, int keep_codeword,
+                                   uint32_t* h_commit8, sp1b200_commit** out);
+void sp1b200_commit_free(sp1b200_ctx* ctx, sp1b200_commit* c);
+
+/* Stacked-PCS + BaseFold evaluation proof at `point` (n_point ext elements, the last log_stacking_height of
+ * which are the stack point) over `n_rounds` commitment rounds
+ * (slop/crates/stacked/src/prover.rs:111-160 -> basefold-prover/src/prover.rs:102-270).
+ * h_replay_witnesses: {batch_grinding_witness, pow_witness} when params.grind_mode == 1, else NULL.
+ * Proof is written as flat words in the field order of StackedBasefoldProof/BasefoldProof
+ * (slop/crates/stacked/src/verifier.rs:27-31, slop/crates/basefold/src/verifier.rs:97-116):
+ *   univariate_messages[d][2] ext | fri_commitments[d] digest | per commit round {values[q][ncols], root, log_height,
+ *   width, paths[q][log_height] digest} | per fold round {values[q][8], root, log_height, width, paths} |
+ *   final_poly ext | pow_witness | batch_grinding_witness | batch_evaluations[round][ncols] ext.
+ * *h_proof_words receives the number of words; returns an error if proof_cap_words is too small. */
+sp1b200_err sp1b200_stacked_prove(sp1b200_ctx* ctx, sp1b200_commit* const* rounds, uint32_t n_rounds,
+                                  const uint32_t* h_point, uint32_t n_point, const uint32_t* h_replay_witnesses,
+                                  uint32_t* h_challenger34, uint32_t* h_proof, uint64_t proof_cap_words,
+                                  uint64_t* h_proof_words);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SP1B200_H */

@@ -1,0 +1,178 @@
+// Context, memory and the kernel-level C entry points of include/sp1b200.h.
+#include "ctx.cuh"
+#include <cstdarg>
+#include <cstring>
+
+sp1b200_err sp1b200_init_tables(sp1b200_ctx* ctx);
+sp1b200_err sp1b200_rs_encode_device(sp1b200_ctx*, const uint32_t*, uint64_t, uint32_t, uint32_t, uint32_t*);
+sp1b200_err sp1b200_permute_device(sp1b200_ctx*, uint32_t*, uint64_t);
+sp1b200_err sp1b200_merkle_commit_device(sp1b200_ctx*, const uint32_t*, uint64_t, uint32_t, uint32_t*, uint32_t*);
+
+static thread_local char g_err[1024];
+
+const char* sp1b200_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return g_err;
+}
+
+bool sp1b200_is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+sp1b200_err DevBuf::in(sp1b200_ctx* c, const void* any, size_t nbytes) {
+    ctx = c; bytes = nbytes;
+    if (nbytes == 0) { d = nullptr; return nullptr; }
+    if (sp1b200_is_device_ptr(any)) { d = const_cast<void*>(any); owned = false; return nullptr; }
+    SP1_CUDA(cudaMallocAsync(&d, nbytes, c->stream));
+    owned = true;
+    SP1_CUDA(cudaMemcpyAsync(d, any, nbytes, cudaMemcpyHostToDevice, c->stream));
+    return nullptr;
+}
+sp1b200_err DevBuf::out(sp1b200_ctx* c, void* any, size_t nbytes) {
+    ctx = c; bytes = nbytes;
+    if (nbytes == 0) { d = nullptr; return nullptr; }
+    if (sp1b200_is_device_ptr(any)) { d = any; owned = false; return nullptr; }
+    SP1_CUDA(cudaMallocAsync(&d, nbytes, c->stream));
+    owned = true; host = any;
+    return nullptr;
+}
+sp1b200_err DevBuf::finish() {
+    if (owned && host) {
+        SP1_CUDA(cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        SP1_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (owned) { cudaFreeAsync(d, ctx->stream); owned = false; }
+    return nullptr;
+}
+DevBuf::~DevBuf() {
+    if (owned) cudaFreeAsync(d, ctx->stream);
+}
+
+extern "C" {
+
+const char* sp1b200_version(void) { return "sp1-b200 0.1 (sp1 v6.4.0 hypercube core-shard path, sm_100a)"; }
+
+void sp1b200_default_core_params(sp1b200_params* p) {
+    p->log_stacking_height = 21; p->max_log_row_count = 22; p->log_blowup = 2; p->num_queries = 124;
+    p->pow_bits = 16; p->batch_pow_bits = 5; p->gkr_pow_bits = 12; p->grind_mode = 0;
+}
+
+sp1b200_err sp1b200_ctx_create(int device, const sp1b200_params* params, sp1b200_ctx** out) {
+    if (!out) return sp1b200_set_error("ctx_create: out is NULL");
+    int ndev = 0;
+    SP1_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return sp1b200_set_error("ctx_create: device %d not present (%d devices)", device, ndev);
+    SP1_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SP1_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return sp1b200_set_error("ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    sp1b200_ctx* c = new sp1b200_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    if (params) c->params = *params; else sp1b200_default_core_params(&c->params);
+    SP1_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SP1_CUDA(cudaEventCreate(&c->ev0));
+    SP1_CUDA(cudaEventCreate(&c->ev1));
+    // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    SP1_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    SP1_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    sp1b200_err e = sp1b200_init_tables(c);
+    if (e) { delete c; return e; }
+    SP1_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return nullptr;
+}
+
+void sp1b200_ctx_destroy(sp1b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_TH); cudaFree(c->d_TL);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+sp1b200_err sp1b200_ctx_sync(sp1b200_ctx* c) { SP1_CUDA(cudaStreamSynchronize(c->stream)); return nullptr; }
+void* sp1b200_ctx_stream(sp1b200_ctx* c) { return (void*)c->stream; }
+uint64_t sp1b200_launch_count(sp1b200_ctx* c) { return c->launches; }
+float sp1b200_last_phase_ms(sp1b200_ctx* c, const char* phase) {
+    auto it = c->phase_ms.find(phase);
+    return it == c->phase_ms.end() ? -1.0f : it->second;
+}
+
+sp1b200_err sp1b200_malloc(sp1b200_ctx* c, size_t bytes, void** d_out) {
+    SP1_CUDA(cudaMallocAsync(d_out, bytes, c->stream));
+    return nullptr;
+}
+sp1b200_err sp1b200_free(sp1b200_ctx* c, void* d_ptr) {
+    if (d_ptr) SP1_CUDA(cudaFreeAsync(d_ptr, c->stream));
+    return nullptr;
+}
+sp1b200_err sp1b200_memcpy_h2d(sp1b200_ctx* c, void* d_dst, const void* h_src, size_t bytes) {
+    SP1_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return nullptr;
+}
+sp1b200_err sp1b200_memcpy_d2h(sp1b200_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
+    SP1_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SP1_CUDA(cudaStreamSynchronize(c->stream));
+    return nullptr;
+}
+
+sp1b200_err sp1b200_poseidon2_permute(sp1b200_ctx* c, uint32_t* states_any, uint64_t n) {
+    DevBuf b;
+    SP1_TRY(b.in(c, states_any, n * 16 * sizeof(uint32_t)));
+    if (b.owned) b.host = states_any;
+    PhaseTimer t(c, "poseidon2_permute");
+    SP1_TRY(sp1b200_permute_device(c, (uint32_t*)b.d, n));
+    t.stop();
+    return b.finish();
+}
+
+sp1b200_err sp1b200_rs_encode(sp1b200_ctx* c, const uint32_t* msg_any, uint64_t ncols, uint32_t log_h, uint32_t log_blowup,
+                              uint32_t* out_any) {
+    DevBuf in, out;
+    size_t n = (size_t)ncols << log_h;
+    SP1_TRY(in.in(c, msg_any, n * sizeof(uint32_t)));
+    SP1_TRY(out.out(c, out_any, (n << log_blowup) * sizeof(uint32_t)));
+    PhaseTimer t(c, "rs_encode");
+    SP1_TRY(sp1b200_rs_encode_device(c, (const uint32_t*)in.d, ncols, log_h, log_blowup, (uint32_t*)out.d));
+    t.stop();
+    SP1_TRY(out.finish());
+    return in.finish();
+}
+
+sp1b200_err sp1b200_merkle_commit(sp1b200_ctx* c, const uint32_t* mat_any, uint64_t width, uint32_t log_h, uint32_t* d_layers_out,
+                                  uint32_t* h_root8, uint32_t* h_commit8) {
+    DevBuf in;
+    SP1_TRY(in.in(c, mat_any, ((size_t)width << log_h) * sizeof(uint32_t)));
+    uint32_t* layers = d_layers_out;
+    size_t nd = ((size_t)2 << log_h) - 1;
+    if (!layers) SP1_CUDA(cudaMallocAsync((void**)&layers, nd * 8 * sizeof(uint32_t), c->stream));
+    uint32_t* d_rc;
+    SP1_CUDA(cudaMallocAsync((void**)&d_rc, 16 * sizeof(uint32_t), c->stream));
+    PhaseTimer t(c, "merkle_commit");
+    sp1b200_err e = sp1b200_merkle_commit_device(c, (const uint32_t*)in.d, width, log_h, layers, d_rc);
+    t.stop();
+    uint32_t rc[16];
+    if (!e) {
+        cudaError_t ce = cudaMemcpyAsync(rc, d_rc, sizeof(rc), cudaMemcpyDeviceToHost, c->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+        if (ce != cudaSuccess) e = sp1b200_set_error("merkle_commit: %s", cudaGetErrorString(ce));
+    }
+    cudaFreeAsync(d_rc, c->stream);
+    if (!d_layers_out) cudaFreeAsync(layers, c->stream);
+    if (e) return e;
+    if (h_root8) memcpy(h_root8, rc, 32);
+    if (h_commit8) memcpy(h_commit8, rc + 8, 32);
+    return in.finish();
+}
+
+}  // extern "C"

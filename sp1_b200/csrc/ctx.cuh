@@ -1,0 +1,77 @@
+// Context / runtime shared by all kernels: one CUDA stream, stream-ordered pool allocations,
+// root-of-unity tables, launch counter and per-phase CUDA-event timing.
+// Replaces the role of sp1-gpu/crates/cuda (TaskScope = stream + cudaMallocAsync pool) and
+// sp1-gpu/crates/sys/lib/runtime/{stream,memory,mem_pool}.cu for this path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/sp1b200.h"
+
+struct sp1b200_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    sp1b200_params params{};
+    // TH[i] = w^(i * 2^12), TL[j] = w^j  with w = two-adic generator of order 2^24 (Montgomery words)
+    uint32_t* d_TH = nullptr;
+    uint32_t* d_TL = nullptr;
+    uint64_t launches = 0;
+    std::map<std::string, float> phase_ms;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+const char* sp1b200_set_error(const char* fmt, ...);
+
+#define SP1_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return sp1b200_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define SP1_TRY(call)                   \
+    do {                                \
+        sp1b200_err _m = (call);        \
+        if (_m) return _m;              \
+    } while (0)
+
+// launch wrapper: counts the launch and checks the launch error
+#define SP1_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+    do {                                                                       \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);       \
+        (ctx)->launches++;                                                     \
+        SP1_CUDA(cudaGetLastError());                                          \
+    } while (0)
+
+struct PhaseTimer {
+    sp1b200_ctx* ctx;
+    const char* name;
+    PhaseTimer(sp1b200_ctx* c, const char* n) : ctx(c), name(n) { cudaEventRecord(c->ev0, c->stream); }
+    // call after the phase's last launch; synchronises the end event
+    void stop() {
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaEventSynchronize(ctx->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->phase_ms[name] = ms;
+    }
+};
+
+// resolves a host-or-device pointer to a device pointer, staging through a temporary if needed
+struct DevBuf {
+    sp1b200_ctx* ctx = nullptr;
+    void* d = nullptr;
+    void* host = nullptr;  // original host pointer if staged
+    size_t bytes = 0;
+    bool owned = false;
+    sp1b200_err in(sp1b200_ctx* c, const void* any, size_t nbytes);        // for inputs (copies H2D if host)
+    sp1b200_err out(sp1b200_ctx* c, void* any, size_t nbytes);             // for outputs (allocates if host)
+    sp1b200_err finish();                                                  // D2H copy-back for outputs, free
+    ~DevBuf();
+};
+
+bool sp1b200_is_device_ptr(const void* p);

@@ -1,0 +1,170 @@
+"""ctypes binding of libsp1b200.so (the C ABI declared in include/sp1b200.h).
+
+Mirrors what the Rust shim of INTEGRATION.md binds.  No compute happens in Python and there is no
+fallback path: a missing library or a failing call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libsp1b200.so")
+
+u32p = C.POINTER(C.c_uint32)
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("log_stacking_height", "max_log_row_count", "log_blowup", "num_queries",
+                                          "pow_bits", "batch_pow_bits", "gkr_pow_bits", "grind_mode")]
+
+
+DEFAULT_CORE_PARAMS = dict(log_stacking_height=21, max_log_row_count=22, log_blowup=2, num_queries=124, pow_bits=16,
+                           batch_pow_bits=5, gkr_pow_bits=12, grind_mode=0)
+
+
+class Sp1B200Error(RuntimeError):
+    pass
+
+
+_cdll = None
+
+
+def load():
+    """dlopen the library (no CUDA call is made).  Raises if it has not been built."""
+    global _cdll
+    if _cdll is None:
+        if not os.path.exists(SO_PATH):
+            raise Sp1B200Error(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(SO_PATH)
+        L.sp1b200_version.restype = C.c_char_p
+        L.sp1b200_ctx_stream.restype = C.c_void_p
+        L.sp1b200_launch_count.restype = C.c_uint64
+        L.sp1b200_last_phase_ms.restype = C.c_float
+        L.sp1b200_challenger_sample_bits.restype = C.c_uint32
+        L.sp1b200_challenger_check_witness.restype = C.c_int
+        for name in ERR_FUNCS:
+            getattr(L, name).restype = C.c_char_p
+        _cdll = L
+    return _cdll
+
+
+# every symbol include/sp1b200.h declares (tests/test_abi.py checks the header against this list and the .so)
+ERR_FUNCS = [
+    "sp1b200_ctx_create", "sp1b200_ctx_sync", "sp1b200_malloc", "sp1b200_free", "sp1b200_memcpy_h2d",
+    "sp1b200_memcpy_d2h", "sp1b200_poseidon2_permute", "sp1b200_rs_encode", "sp1b200_merkle_commit", "sp1b200_grind",
+    "sp1b200_stacked_commit", "sp1b200_stacked_prove",
+]
+OTHER_FUNCS = ["sp1b200_challenger_init", "sp1b200_challenger_observe", "sp1b200_challenger_sample",
+               "sp1b200_challenger_sample_bits", "sp1b200_challenger_check_witness", "sp1b200_ctx_destroy", "sp1b200_default_core_params", "sp1b200_version", "sp1b200_ctx_stream",
+               "sp1b200_launch_count", "sp1b200_last_phase_ms", "sp1b200_commit_free"]
+
+
+def _ptr(a):
+    """numpy uint32 array or torch tensor (cpu or cuda) or int address -> c_void_p"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"], "need contiguous uint32"
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):  # torch tensor (int32/uint32 storage)
+        assert a.is_contiguous() and a.element_size() == 4
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class Lib:
+    """One context = one GPU + one stream (reference: one prover process per GPU, crates/cuda/src/server.rs:36-45)."""
+
+    def __init__(self, device=0, **params):
+        self.L = load()
+        p = dict(DEFAULT_CORE_PARAMS)
+        p.update(params)
+        self.params = p
+        self._p = Params(**p)
+        self.ctx = C.c_void_p()
+        self._chk(self.L.sp1b200_ctx_create(C.c_int(device), C.byref(self._p), C.byref(self.ctx)))
+
+    def _chk(self, err):
+        if err:
+            raise Sp1B200Error(err.decode())
+
+    def close(self):
+        if self.ctx:
+            self.L.sp1b200_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- runtime ---------------------------------------------------------------------------------------------
+    def sync(self):
+        self._chk(self.L.sp1b200_ctx_sync(self.ctx))
+
+    def stream(self):
+        return self.L.sp1b200_ctx_stream(self.ctx)
+
+    def launch_count(self):
+        return int(self.L.sp1b200_launch_count(self.ctx))
+
+    def phase_ms(self, name):
+        return float(self.L.sp1b200_last_phase_ms(self.ctx, name.encode()))
+
+    # -- kernel-level ---------------------------------------------------------------------------------------
+    def poseidon2_permute(self, states):
+        n = states.shape[0] if hasattr(states, "shape") else None
+        self._chk(self.L.sp1b200_poseidon2_permute(self.ctx, _ptr(states), C.c_uint64(n)))
+        return states
+
+    def rs_encode(self, msg, out, ncols, log_h, log_blowup=None):
+        lb = self.params["log_blowup"] if log_blowup is None else log_blowup
+        self._chk(self.L.sp1b200_rs_encode(self.ctx, _ptr(msg), C.c_uint64(ncols), C.c_uint32(log_h), C.c_uint32(lb),
+                                           _ptr(out)))
+        return out
+
+    def merkle_commit(self, mat, width, log_h, d_layers=None):
+        root = np.zeros(8, np.uint32)
+        commit = np.zeros(8, np.uint32)
+        self._chk(self.L.sp1b200_merkle_commit(self.ctx, _ptr(mat), C.c_uint64(width), C.c_uint32(log_h), _ptr(d_layers),
+                                               _ptr(root), _ptr(commit)))
+        return root, commit
+
+    def grind(self, state34, bits):
+        st = np.ascontiguousarray(state34, dtype=np.uint32).copy()
+        w = C.c_uint32()
+        self._chk(self.L.sp1b200_grind(self.ctx, _ptr(st), C.c_uint32(bits), C.byref(w)))
+        return int(w.value), st
+
+
+class HostChallenger:
+    """The library's host transcript object on the 34-word state (no GPU needed)."""
+
+    def __init__(self, state=None):
+        self.L = load()
+        self.st = np.zeros(34, np.uint32)
+        if state is not None:
+            self.st[:] = state
+
+    def clone(self):
+        return HostChallenger(self.st.copy())
+
+    def observe(self, vals):
+        v = np.ascontiguousarray(np.atleast_1d(vals), dtype=np.uint32)
+        self.L.sp1b200_challenger_observe(_ptr(self.st), _ptr(v), C.c_uint64(v.size))
+
+    def sample(self, n=1):
+        out = np.zeros(n, np.uint32)
+        self.L.sp1b200_challenger_sample(_ptr(self.st), _ptr(out), C.c_uint64(n))
+        return out
+
+    def sample_bits(self, bits):
+        return int(self.L.sp1b200_challenger_sample_bits(_ptr(self.st), C.c_uint32(bits)))
+
+    def check_witness(self, bits, w):
+        return bool(self.L.sp1b200_challenger_check_witness(_ptr(self.st), C.c_uint32(bits), C.c_uint32(w)))

@@ -41,6 +41,7 @@ __global__ void grind_finalize_kernel(uint32_t* __restrict__ st, uint32_t w) {
     const uint32_t nin = st[32];
     for (uint32_t i = 0; i < nin; i++) s[i] = st[16 + i];
     s[nin] = kb::from_canonical(w);
+    st[16 + nin] = s[nin];  // the observed witness stays in the (logically empty) input buffer words
     p2::permute(s);
     for (int i = 0; i < 16; i++) st[i] = s[i];
     for (int i = 0; i < 8; i++) st[24 + i] = s[i];

@@ -2,6 +2,7 @@
 #include "ctx.cuh"
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 
 sp1b200_err sp1b200_init_tables(sp1b200_ctx* ctx);
 sp1b200_err sp1b200_rs_encode_device(sp1b200_ctx*, const uint32_t*, uint64_t, uint32_t, uint32_t, uint32_t*);
@@ -75,6 +76,7 @@ sp1b200_err sp1b200_ctx_create(int device, const sp1b200_params* params, sp1b200
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     if (params) c->params = *params; else sp1b200_default_core_params(&c->params);
+    { const char* g = getenv("SP1B200_GENERIC_NTT"); c->force_generic_ntt = g && g[0] == '1'; }
     SP1_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SP1_CUDA(cudaEventCreate(&c->ev0));
     SP1_CUDA(cudaEventCreate(&c->ev1));

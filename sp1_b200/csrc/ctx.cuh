@@ -20,6 +20,7 @@ struct sp1b200_ctx {
     uint32_t* d_TH = nullptr;
     uint32_t* d_TL = nullptr;
     uint64_t launches = 0;
+    bool force_generic_ntt = false;  // SP1B200_GENERIC_NTT=1: reference (slow) kernels, used to cross-check the fast path
     std::map<std::string, float> phase_ms;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -50,15 +51,23 @@ const char* sp1b200_set_error(const char* fmt, ...);
 struct PhaseTimer {
     sp1b200_ctx* ctx;
     const char* name;
-    PhaseTimer(sp1b200_ctx* c, const char* n) : ctx(c), name(n) { cudaEventRecord(c->ev0, c->stream); }
-    // call after the phase's last launch; synchronises the end event
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool done = false;
+    PhaseTimer(sp1b200_ctx* c, const char* n) : ctx(c), name(n) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, c->stream);
+    }
+    // call after the phase's last launch; synchronises on the end event
     void stop() {
-        cudaEventRecord(ctx->ev1, ctx->stream);
-        cudaEventSynchronize(ctx->ev1);
+        if (done) return;
+        done = true;
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
         float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        cudaEventElapsedTime(&ms, e0, e1);
         ctx->phase_ms[name] = ms;
     }
+    ~PhaseTimer() { cudaEventDestroy(e0); cudaEventDestroy(e1); }
 };
 
 // resolves a host-or-device pointer to a device pointer, staging through a temporary if needed

@@ -1,0 +1,87 @@
+// Host-side KoalaBear / ext4 scalar arithmetic used by the library's transcript driver (a few hundred
+// operations per proof: batching coefficients, claimed sums, round-polynomial bookkeeping).  Product code,
+// independent of oracle/.  Same representation as the device code (Montgomery words).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace hf {
+
+constexpr uint32_t P = 0x7f000001u;
+constexpr uint32_t MPRIME = 0x7effffffu;
+constexpr uint32_t ONE = 0x01fffffeu;
+
+inline uint32_t reduce(uint64_t x) {
+    uint32_t m = (uint32_t)x * MPRIME;
+    uint64_t u = x + (uint64_t)m * P;
+    uint32_t r = (uint32_t)(u >> 32);
+    return r >= P ? r - P : r;
+}
+inline uint32_t add(uint32_t a, uint32_t b) { uint32_t s = a + b; return s >= P ? s - P : s; }
+inline uint32_t sub(uint32_t a, uint32_t b) { return a >= b ? a - b : a + P - b; }
+inline uint32_t neg(uint32_t a) { return a ? P - a : 0; }
+inline uint32_t mul(uint32_t a, uint32_t b) { return reduce((uint64_t)a * b); }
+inline uint32_t to_monty(uint64_t c) { return (uint32_t)(((c % P) << 32) % P); }
+inline uint32_t from_monty(uint32_t m) { return reduce(m); }
+inline uint32_t pow(uint32_t b, uint64_t e) {
+    uint32_t r = ONE;
+    while (e) { if (e & 1) r = mul(r, b); b = mul(b, b); e >>= 1; }
+    return r;
+}
+inline uint32_t inv(uint32_t a) { return pow(a, P - 2); }
+
+struct E4 {
+    uint32_t c[4] = {0, 0, 0, 0};
+    static E4 one() { E4 r; r.c[0] = ONE; return r; }
+    static E4 from_base(uint32_t a) { E4 r; r.c[0] = a; return r; }
+    static E4 load(const uint32_t* p) { E4 r; for (int i = 0; i < 4; i++) r.c[i] = p[i]; return r; }
+    void store(uint32_t* p) const { for (int i = 0; i < 4; i++) p[i] = c[i]; }
+    bool operator==(const E4& o) const { return c[0] == o.c[0] && c[1] == o.c[1] && c[2] == o.c[2] && c[3] == o.c[3]; }
+    bool is_zero() const { return !(c[0] | c[1] | c[2] | c[3]); }
+};
+inline E4 operator+(const E4& a, const E4& b) { E4 r; for (int i = 0; i < 4; i++) r.c[i] = add(a.c[i], b.c[i]); return r; }
+inline E4 operator-(const E4& a, const E4& b) { E4 r; for (int i = 0; i < 4; i++) r.c[i] = sub(a.c[i], b.c[i]); return r; }
+inline E4 operator*(const E4& a, uint32_t s) { E4 r; for (int i = 0; i < 4; i++) r.c[i] = mul(a.c[i], s); return r; }
+inline E4 operator*(const E4& a, const E4& b) {
+    uint32_t t[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) t[i + j] = add(t[i + j], mul(a.c[i], b.c[j]));
+    const uint32_t three = to_monty(3);
+    E4 r;
+    r.c[0] = add(t[0], mul(three, t[4]));
+    r.c[1] = add(t[1], mul(three, t[5]));
+    r.c[2] = add(t[2], mul(three, t[6]));
+    r.c[3] = t[3];
+    return r;
+}
+inline E4 inv(const E4& a) {
+    // Frobenius-free inverse via the tower F[y]/(y^2-3) (y = x^2)
+    const uint32_t three = to_monty(3);
+    uint32_t A0 = a.c[0], A1 = a.c[2], B0 = a.c[1], B1 = a.c[3];
+    uint32_t n0 = sub(add(mul(A0, A0), mul(three, mul(A1, A1))), mul(three, add(mul(B0, B1), mul(B0, B1))));
+    uint32_t n1 = sub(add(mul(A0, A1), mul(A0, A1)), add(mul(B0, B0), mul(three, mul(B1, B1))));
+    uint32_t d = inv(sub(mul(n0, n0), mul(three, mul(n1, n1))));
+    uint32_t i0 = mul(n0, d), i1 = neg(mul(n1, d));
+    E4 conj; conj.c[0] = A0; conj.c[1] = neg(B0); conj.c[2] = A1; conj.c[3] = neg(B1);
+    E4 s; s.c[0] = i0; s.c[2] = i1;
+    return conj * s;
+}
+
+// eq(point, i), point[0] <-> MSB of i  (slop/crates/multilinear/src/lagrange.rs:19-45)
+inline std::vector<E4> partial_lagrange(const std::vector<E4>& point) {
+    std::vector<E4> ev{E4::one()};
+    for (const E4& x : point) {
+        std::vector<E4> nx(ev.size() * 2);
+        for (size_t i = 0; i < ev.size(); i++) {
+            E4 pr = ev[i] * x;
+            nx[2 * i] = ev[i] - pr;
+            nx[2 * i + 1] = pr;
+        }
+        ev.swap(nx);
+    }
+    return ev;
+}
+
+inline unsigned log2_ceil(uint64_t n) { unsigned k = 0; while (((uint64_t)1 << k) < n) k++; return k; }
+
+}  // namespace hf

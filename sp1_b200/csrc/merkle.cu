@@ -111,3 +111,20 @@ sp1b200_err sp1b200_merkle_commit_device(sp1b200_ctx* ctx, const uint32_t* d_mat
     SP1_LAUNCH(ctx, tcs_commitment_kernel, 1, 32, 0, d_layers + off * 8, log_h, (uint32_t)width, d_root_commit16);
     return nullptr;
 }
+
+// d_layers: leaf layer (2^log_h digests) already filled; builds the compress layers above it and
+// root/commitment with the given matrix width
+sp1b200_err sp1b200_merkle_tree_from_leaves_device(sp1b200_ctx* ctx, uint32_t* d_layers, uint32_t log_h, uint32_t width,
+                                                   uint32_t* d_root_commit16) {
+    const uint64_t h = (uint64_t)1 << log_h;
+    uint64_t off = 0;
+    for (uint32_t k = 1; k <= log_h; k++) {
+        uint64_t n_par = h >> k;
+        uint32_t* children = d_layers + off * 8;
+        uint32_t* parents = d_layers + (off + (h >> (k - 1))) * 8;
+        SP1_LAUNCH(ctx, compress_layer_kernel, (unsigned)((n_par + 255) / 256), 256, 0, children, parents, n_par);
+        off += h >> (k - 1);
+    }
+    SP1_LAUNCH(ctx, tcs_commitment_kernel, 1, 32, 0, d_layers + off * 8, log_h, width, d_root_commit16);
+    return nullptr;
+}

@@ -108,7 +108,178 @@ __global__ void rs_step_b_generic(uint32_t* __restrict__ buf, int L1, int L2, in
     for (int lo = threadIdx.x; lo < W; lo += blockDim.x) row[lo] = sm[lo];
 }
 
+// ==== fast path: radix-8 butterflies in registers, 2-3 shared-memory exchanges per transform =================
+
+// (a - c) * w with the difference left unreduced in (0, 2p): valid Montgomery operand since w < p
+__device__ __forceinline__ uint32_t submul(uint32_t a, uint32_t c, uint32_t w) { return kb::mul(a - c + kb::P, w); }
+
+// in-place radix-8 decimation-in-frequency butterfly on v[0..8) (v[j], j bit 2 = most significant of the 3 index bits)
+__device__ __forceinline__ void dif8(uint32_t (&v)[8], const uint32_t (&wA)[4], const uint32_t (&wB)[2], uint32_t wC) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) { uint32_t a = v[j], c = v[j + 4]; v[j] = kb::add(a, c); v[j + 4] = submul(a, c, wA[j]); }
+#pragma unroll
+    for (int h = 0; h < 8; h += 4)
+#pragma unroll
+        for (int j = 0; j < 2; j++) { uint32_t a = v[h + j], c = v[h + j + 2]; v[h + j] = kb::add(a, c); v[h + j + 2] = submul(a, c, wB[j]); }
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) { uint32_t a = v[h], c = v[h + 1]; v[h] = kb::add(a, c); v[h + 1] = submul(a, c, wC); }
+}
+
+// twiddles for a radix-8 pass whose top stage has 2^s points and whose elements are spaced `stride` apart:
+// local element j sits at offset j*stride + low inside its 2^s block  (stride = 2^(s-3))
+__device__ __forceinline__ void load_tw8(const uint32_t* __restrict__ TH, int s, uint32_t low, uint32_t (&wA)[4], uint32_t (&wB)[2],
+                                         uint32_t& wC) {
+    const uint32_t stride = 1u << (s - 3);
+#pragma unroll
+    for (int j = 0; j < 4; j++) wA[j] = __ldg(TH + ((j * stride + low) << (12 - s)));
+#pragma unroll
+    for (int j = 0; j < 2; j++) wB[j] = __ldg(TH + ((j * stride + low) << (13 - s)));
+    wC = __ldg(TH + (low << (14 - s)));
+}
+
+// ---- fast step B: one 2048-point row per block of 256 threads, in place --------------------------------
+__device__ __forceinline__ int swzB(int e) { return e ^ (((e >> 5) & 7) << 2); }
+
+__global__ void __launch_bounds__(256) rs_step_b_2048(uint32_t* __restrict__ buf, int L1, int b, const uint32_t* __restrict__ TH,
+                                                      const uint32_t* __restrict__ TL) {
+    __shared__ uint32_t sm[2048];
+    constexpr int L2 = 11;
+    const int L = L1 + L2;
+    const size_t M = (size_t)1 << (L + b);
+    const uint32_t q = blockIdx.x;
+    const uint32_t ka = (L1 + b) ? (__brev(q) >> (32 - (L1 + b))) : 0;
+    uint32_t* row = buf + (size_t)blockIdx.y * M + ((size_t)q << L2);
+    const int t = threadIdx.x;
+    uint32_t v[8], wA[4], wB[2], wC;
+    // pass 1: bits 10..8, straight from global, with the inter-step twist omega^(lo * ka)
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = row[j * 256 + t];
+    if (ka) {
+        const int sh = 24 - L - b;
+        uint32_t tw = root_pow(TH, TL, ((uint32_t)t * ka) << sh);
+        const uint32_t step = root_pow(TH, TL, ((256u * ka) << sh) & 0xffffffu);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { v[j] = kb::mul(v[j], tw); if (j < 7) tw = kb::mul(tw, step); }
+    }
+    load_tw8(TH, 11, t, wA, wB, wC);
+    dif8(v, wA, wB, wC);
+#pragma unroll
+    for (int j = 0; j < 8; j++) sm[swzB(j * 256 + t)] = v[j];
+    __syncthreads();
+    // pass 2: bits 7..5
+    {
+        const int low = t & 31, hib = t >> 5;
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = sm[swzB(hib * 256 + j * 32 + low)];
+        load_tw8(TH, 8, low, wA, wB, wC);
+        dif8(v, wA, wB, wC);
+#pragma unroll
+        for (int j = 0; j < 8; j++) sm[swzB(hib * 256 + j * 32 + low)] = v[j];
+    }
+    __syncthreads();
+    // pass 3: bits 4..2
+    {
+        const int low = t & 3, hib = t >> 2;
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = sm[swzB(hib * 32 + j * 4 + low)];
+        load_tw8(TH, 5, low, wA, wB, wC);
+        dif8(v, wA, wB, wC);
+#pragma unroll
+        for (int j = 0; j < 8; j++) sm[swzB(hib * 32 + j * 4 + low)] = v[j];
+    }
+    __syncthreads();
+    // pass 4: bits 1..0 (radix 4, only non-trivial twiddle is the 4th root), two groups per thread, 16-byte I/O
+    const uint32_t w4 = __ldg(TH + 1024);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int g = t + k * 256;
+        uint4 x = *reinterpret_cast<const uint4*>(&sm[swzB(4 * g)]);
+        uint32_t a0 = kb::add(x.x, x.z), a1 = kb::add(x.y, x.w);
+        uint32_t a2 = kb::sub(x.x, x.z), a3 = submul(x.y, x.w, w4);
+        uint4 y = make_uint4(kb::add(a0, a1), kb::sub(a0, a1), kb::add(a2, a3), kb::sub(a2, a3));
+        *reinterpret_cast<uint4*>(row + 4 * g) = y;
+    }
+}
+
+// ---- fast step A: tile of 8 consecutive lo x all 2^L1 hi, L1 = 3*NP + 1, 2^L1 threads ----------------------
+__device__ __forceinline__ int swzA(int e) { return e ^ (((e >> 7) & 1) << 4); }
+
+template <int L1>
+__global__ void __launch_bounds__(1 << L1) rs_step_a_fast(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int L2, int b,
+                                                          const uint32_t* __restrict__ TH, const uint32_t* __restrict__ TL) {
+    static_assert(L1 % 3 == 1 && L1 >= 7, "L1 = 3k+1, at least two radix-8 passes");
+    constexpr int NP = L1 / 3;           // radix-8 passes; the last stage (hi bit 0) is a warp shuffle
+    constexpr int TILE = 8 << L1;
+    extern __shared__ uint32_t smA[];    // 2 x TILE words (double buffer across cosets)
+    const int L = L1 + L2;
+    const size_t n = (size_t)1 << L, M = n << b;
+    const uint32_t* col_in = in + (size_t)blockIdx.y * n;
+    uint32_t* col_out = out + (size_t)blockIdx.y * M;
+    const uint32_t lo0 = blockIdx.x * 8;
+    const int u = threadIdx.x, lo = u & 7, x = u >> 3;  // x: low L1-3 bits of hi in pass-1 layout
+    uint32_t src[8], v[8], wA[4], wB[2], wC;
+#pragma unroll
+    for (int j = 0; j < 8; j++) src[j] = col_in[((size_t)(j * (1 << (L1 - 3)) + x) << L2) + lo0 + lo];
+    const int sh = 24 - L1 - b;
+    for (int r = 0; r < (1 << b); r++) {
+        uint32_t* sm = smA + (r & 1) * TILE;
+        const uint32_t rr = __brev((uint32_t)r) >> (32 - b);
+        if (r == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = src[j];
+        } else {
+            uint32_t tw = root_pow(TH, TL, ((uint32_t)x * r) << sh);
+            const uint32_t step = root_pow(TH, TL, ((uint32_t)r << (L1 - 3)) << sh);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { v[j] = kb::mul(src[j], tw); if (j < 7) tw = kb::mul(tw, step); }
+        }
+        // pass 0: hi bits L1-1 .. L1-3
+        load_tw8(TH, L1, x, wA, wB, wC);
+        dif8(v, wA, wB, wC);
+#pragma unroll
+        for (int j = 0; j < 8; j++) sm[swzA(j * (TILE / 8) + u)] = v[j];
+        __syncthreads();
+#pragma unroll
+        for (int k = 1; k < NP; k++) {
+            const int hb = L1 - 1 - 3 * k;            // top hi bit of this pass
+            const int nlow = hb - 2;                  // hi bits below the pass
+            const int low = x & ((1 << nlow) - 1), high = x >> nlow;
+            const int base = ((high << (hb + 1)) + low) * 8 + lo;
+            const int stride = 8 << nlow;
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = sm[swzA(base + j * stride)];
+            load_tw8(TH, hb + 1, low, wA, wB, wC);
+            dif8(v, wA, wB, wC);
+            if (k < NP - 1) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) sm[swzA(base + j * stride)] = v[j];
+                __syncthreads();
+            } else {
+                // last stage: hi bit 0 lives in bit 3 of the thread index -> partner lane = lane ^ 8, twiddle 1
+                const bool odd = (x & 1);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    uint32_t o = __shfl_xor_sync(0xffffffffu, v[j], 8);
+                    uint32_t res = odd ? kb::sub(o, v[j]) : kb::add(v[j], o);
+                    const uint32_t p = (uint32_t)((high << 4) + j * 2 + (x & 1));
+                    col_out[((((size_t)rr << L1) + p) << L2) + lo0 + lo] = res;
+                }
+            }
+        }
+        // double buffering: the next coset writes the other half; the barrier after its pass 0 protects reuse
+    }
+}
+
 }  // namespace
+
+template <int L1>
+static sp1b200_err launch_step_a_fast(sp1b200_ctx* ctx, const uint32_t* in, uint32_t* out, int L2, int b, unsigned nc) {
+    const size_t smem = 2 * (size_t)(8 << L1) * sizeof(uint32_t);
+    SP1_CUDA(cudaFuncSetAttribute(rs_step_a_fast<L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 g((1u << L2) / 8, nc);
+    SP1_LAUNCH(ctx, rs_step_a_fast<L1>, g, 1 << L1, smem, in, out, L2, b, ctx->d_TH, ctx->d_TL);
+    return nullptr;
+}
 
 sp1b200_err sp1b200_init_tables(sp1b200_ctx* ctx) {
     SP1_CUDA(cudaMalloc(&ctx->d_TH, 4096 * sizeof(uint32_t)));
@@ -144,11 +315,15 @@ sp1b200_err sp1b200_rs_encode_device(sp1b200_ctx* ctx, const uint32_t* d_msg, ui
     int threadsB = (1 << L2) / 2;
     if (threadsB > 1024) threadsB = 1024;
     if (threadsB < 32) threadsB = 32;
+    const bool fast = (L2 == 11) && !ctx->force_generic_ntt;
     for (uint64_t c0 = 0; c0 < ncols; c0 += group) {
         unsigned nc = (unsigned)((ncols - c0 < group) ? (ncols - c0) : group);
         dim3 gA((1u << L2) / T, nc), gB(1u << (L1 + b), nc);
-        SP1_LAUNCH(ctx, rs_step_a_generic, gA, threadsA, smemA, d_msg + c0 * n, d_out + c0 * M, L1, L2, b, T, ctx->d_TH, ctx->d_TL);
-        SP1_LAUNCH(ctx, rs_step_b_generic, gB, threadsB, smemB, d_out + c0 * M, L1, L2, b, ctx->d_TH, ctx->d_TL);
+        if (fast && L1 == 10) SP1_TRY(launch_step_a_fast<10>(ctx, d_msg + c0 * n, d_out + c0 * M, L2, b, nc));
+        else if (fast && L1 == 7) SP1_TRY(launch_step_a_fast<7>(ctx, d_msg + c0 * n, d_out + c0 * M, L2, b, nc));
+        else SP1_LAUNCH(ctx, rs_step_a_generic, gA, threadsA, smemA, d_msg + c0 * n, d_out + c0 * M, L1, L2, b, T, ctx->d_TH, ctx->d_TL);
+        if (fast) SP1_LAUNCH(ctx, rs_step_b_2048, gB, 256, 0, d_out + c0 * M, L1, b, ctx->d_TH, ctx->d_TL);
+        else SP1_LAUNCH(ctx, rs_step_b_generic, gB, threadsB, smemB, d_out + c0 * M, L1, L2, b, ctx->d_TH, ctx->d_TL);
     }
     return nullptr;
 }

@@ -135,6 +135,31 @@ class Lib:
                                                _ptr(root), _ptr(commit)))
         return root, commit
 
+    # -- PCS-level ------------------------------------------------------------------------------------------
+    def stacked_commit(self, dense, ncols, keep_codeword=True):
+        """dense: [ncols x 2^log_stacking_height] column-major (numpy or cuda tensor). -> (commit[8], handle)"""
+        commit = np.zeros(8, np.uint32)
+        h = C.c_void_p()
+        self._chk(self.L.sp1b200_stacked_commit(self.ctx, _ptr(dense), C.c_uint64(ncols), C.c_int(int(keep_codeword)),
+                                                _ptr(commit), C.byref(h)))
+        return commit, h
+
+    def commit_free(self, handle):
+        self.L.sp1b200_commit_free(self.ctx, handle)
+
+    def stacked_prove(self, handles, point, challenger_state, replay=None, cap_words=1 << 24):
+        """point: [k,4] uint32 host array; challenger_state: 34 words (updated in place). -> proof words"""
+        n = len(handles)
+        arr = (C.c_void_p * n)(*[h.value for h in handles])
+        point = np.ascontiguousarray(point, dtype=np.uint32)
+        proof = np.zeros(cap_words, np.uint32)
+        nwords = C.c_uint64()
+        rw = None if replay is None else np.ascontiguousarray(replay, dtype=np.uint32)
+        self._chk(self.L.sp1b200_stacked_prove(self.ctx, arr, C.c_uint32(n), _ptr(point), C.c_uint32(point.shape[0]),
+                                               _ptr(rw), _ptr(challenger_state), _ptr(proof), C.c_uint64(cap_words),
+                                               C.byref(nwords)))
+        return proof[:nwords.value].copy()
+
     def grind(self, state34, bits):
         st = np.ascontiguousarray(state34, dtype=np.uint32).copy()
         w = C.c_uint32()

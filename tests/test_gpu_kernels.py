@@ -28,7 +28,10 @@ def test_poseidon2_permute_matches_oracle(lib):
 
 
 @pytest.mark.parametrize("log_h,ncols,lb", [(0, 1, 2), (1, 3, 2), (2, 2, 1), (5, 4, 2), (9, 3, 2), (11, 2, 2), (12, 3, 2),
-                                            (13, 2, 2), (14, 5, 2), (16, 2, 2), (12, 2, 3), (15, 1, 1)])
+                                            (13, 2, 2), (14, 5, 2), (16, 2, 2), (12, 2, 3), (15, 1, 1),
+                                            # register-radix fast path: step B (2048-point rows) alone, with the
+                                            # generic step A, and with the fast step A for L1 = 7 and L1 = 10
+                                            (11, 3, 2), (19, 1, 2), (18, 2, 2), (18, 1, 1), (21, 1, 2), (21, 2, 1)])
 def test_rs_encode_matches_oracle(lib, log_h, ncols, lb):
     rng = np.random.default_rng(100 + log_h)
     msg = O.rand_field(rng, (ncols, 1 << log_h))

@@ -1,7 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see field.hpp header).  PARITY UNPINNED BY STORED FIXTURES.
 // C entry points for tests/ (ctypes), __graft_entry__.smoke() and bench.py's cpu_baseline leg.
 // All field elements cross this boundary as u32 Montgomery words (the reference's in-memory form).
-#include "basefold.hpp"
+#include "jagged.hpp"
 #include <cstdio>
 #include <cstdlib>
 #ifdef _OPENMP
@@ -36,6 +36,25 @@ static void put(std::vector<uint32_t>& o, const BasefoldProof& p) {
 static void put(std::vector<uint32_t>& o, const StackedProof& p) {
     put(o, p.basefold);
     for (auto& r : p.batch_evaluations) for (auto& e : r) put(o, e);
+}
+
+static void put(std::vector<uint32_t>& o, const PartialSumcheckProof& p) {
+    o.push_back((uint32_t)p.polys.size());
+    for (auto& u : p.polys) { o.push_back((uint32_t)u.c.size()); for (auto& c : u.c) put(o, c); }
+    put(o, p.claimed_sum);
+    for (auto& x : p.point) put(o, x);
+    put(o, p.eval);
+}
+// flat word order = field order of slop_jagged::JaggedPcsProof (slop/crates/jagged/src/verifier.rs:17-27)
+static void put(std::vector<uint32_t>& o, const JaggedProof& p) {
+    put(o, p.pcs);
+    put(o, p.sumcheck);
+    put(o, p.jagged_eval);
+    for (auto& v : p.rc_cc) { o.push_back((uint32_t)v.size()); for (auto& rc : v) { o.push_back((uint32_t)rc.first); o.push_back((uint32_t)rc.second); } }
+    for (auto& d : p.merkle_commits) put(o, d);
+    put(o, p.expected_eval);
+    o.push_back(p.max_log_rows);
+    o.push_back(p.log_m);
 }
 
 static void chal_load(Challenger& c, const uint32_t* s) {
@@ -164,6 +183,60 @@ int64_t orc_stacked_prove_verify(const uint32_t* const* dense, const uint64_t* n
     if (err) { std::fprintf(stderr, "oracle verifier rejected oracle proof: %s\n", err); return -1; }
     std::vector<uint32_t> o;
     put(o, sp);
+    if (proof_out) { if (o.size() > proof_cap) return -2; std::copy(o.begin(), o.end(), proof_out); }
+    return (int64_t)o.size();
+}
+
+
+// ---- jagged PCS: commit rounds of tables, prove evaluations at z_row, verify with the restated verifier -----------
+// Round r has n_tables[r] tables; table t of round r: rows[k], cols[k] (k running over all rounds), data at
+// dense[r] + offset (column-major [cols x rows] per table, tables with rows == 0 contribute nothing).
+// z_row: max_log_rows ext elements.  The per-column evaluation claims at z_row (what zerocheck would hand over)
+// are computed here and returned in claims_out (sum over rounds of sum cols, ext each).
+// Returns proof words or a negative value on failure; commits_out: n_rounds x 8 (the jagged commitments).
+int64_t orc_jagged_prove_verify(const uint32_t* const* dense, uint32_t n_rounds, const uint32_t* n_tables, const uint64_t* rows,
+                                const uint64_t* cols, uint32_t log_stack, uint32_t max_log_rows, const uint32_t* z_row_words,
+                                uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits, uint32_t batch_pow_bits,
+                                const uint32_t* replay_witnesses, uint32_t* challenger_state, uint32_t* commits_out,
+                                uint32_t* claims_out, uint32_t* proof_out, uint64_t proof_cap) {
+    FriParams fp; fp.log_blowup = log_blowup; fp.num_queries = num_queries; fp.pow_bits = pow_bits; fp.batch_pow_bits = batch_pow_bits;
+    std::vector<EF> z_row(max_log_rows);
+    for (uint32_t i = 0; i < max_log_rows; i++) z_row[i] = EF::from_base_slice(asF(z_row_words + 4 * i));
+    std::vector<EF> row_eq = partial_lagrange(z_row);
+    std::vector<JaggedRound> rounds;
+    std::vector<std::vector<EF>> claims;
+    std::vector<Digest> commits;
+    size_t k = 0, co = 0;
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        std::vector<Table> tabs;
+        const F* p = asF(dense[r]);
+        std::vector<EF> cl;
+        for (uint32_t t = 0; t < n_tables[r]; t++, k++) {
+            Table tb; tb.rows = rows[k]; tb.cols = cols[k]; tb.data = p;
+            for (size_t c = 0; c < tb.cols; c++) {
+                EF acc;
+                for (size_t i = 0; i < tb.rows; i++) acc += row_eq[i] * p[c * tb.rows + i];
+                cl.push_back(acc);
+            }
+            p += tb.rows * tb.cols;
+            tabs.push_back(tb);
+        }
+        rounds.push_back(jagged_commit(tabs, log_stack, max_log_rows, fp));
+        commits.push_back(rounds.back().commit);
+        for (int i = 0; i < 8; i++) commits_out[r * 8 + i] = commits.back().d[i].v;
+        for (auto& e : cl) for (int i = 0; i < 4; i++) claims_out[co++] = e.c[i].v;
+        claims.push_back(cl);
+    }
+    Challenger ch; chal_load(ch, challenger_state);
+    Challenger vch = ch;
+    F rw[2];
+    if (replay_witnesses) { rw[0] = F::raw(replay_witnesses[0]); rw[1] = F::raw(replay_witnesses[1]); }
+    JaggedProof pf = jagged_prove(z_row, claims, rounds, max_log_rows, ch, fp, replay_witnesses ? rw : nullptr);
+    chal_store(ch, challenger_state);
+    const char* err = jagged_verify(commits, z_row, claims, pf, vch, log_stack, max_log_rows, fp);
+    if (err) { std::fprintf(stderr, "oracle jagged verifier rejected oracle proof: %s\n", err); return -1; }
+    std::vector<uint32_t> o;
+    put(o, pf);
     if (proof_out) { if (o.size() > proof_cap) return -2; std::copy(o.begin(), o.end(), proof_out); }
     return (int64_t)o.size();
 }

@@ -168,3 +168,45 @@ def stacked_prove_verify(dense_rounds, log_h, point, challenger, log_blowup=2, n
     if nwords < 0:
         raise RuntimeError(f"oracle stacked_prove_verify failed ({nwords})")
     return commits, proof[:nwords].copy()
+
+
+def jagged_prove_verify(rounds_tables, log_stack, max_log_rows, z_row, challenger, log_blowup=2, num_queries=124,
+                        pow_bits=16, batch_pow_bits=5, replay=None):
+    """rounds_tables: list (rounds) of lists of tables; a table is an array [cols, rows] (each column contiguous,
+    rows <= 2^max_log_rows; rows may be 0: pass np.zeros((cols, 0))).  z_row: [max_log_rows, 4].
+    Returns (commits [n_rounds, 8], claims [total_cols, 4], proof words); raises if the restated verifier rejects."""
+    n = len(rounds_tables)
+    dense, n_tables, rows, cols = [], [], [], []
+    for tabs in rounds_tables:
+        n_tables.append(len(tabs))
+        parts = []
+        for t in tabs:
+            t = np.ascontiguousarray(t, dtype=np.uint32)
+            cols.append(t.shape[0]); rows.append(t.shape[1])
+            if t.shape[1]:
+                parts.append(t.reshape(-1))
+        dense.append(np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(1, np.uint32))
+    arr = (u32p * n)(*[ptr(d) for d in dense])
+    nt = (C.c_uint32 * n)(*n_tables)
+    R = (C.c_uint64 * len(rows))(*rows)
+    Cc = (C.c_uint64 * len(cols))(*cols)
+    z = np.ascontiguousarray(z_row, dtype=np.uint32)
+    commits = np.zeros((n, 8), np.uint32)
+    claims = np.zeros((sum(cols), 4), np.uint32)
+    cap = 1 << 24
+    proof = np.zeros(cap, np.uint32)
+    rw = None if replay is None else np.ascontiguousarray(replay, dtype=np.uint32)
+    f = lib().orc_jagged_prove_verify
+    f.restype = C.c_int64
+    nwords = f(arr, C.c_uint32(n), nt, R, Cc, C.c_uint32(log_stack), C.c_uint32(max_log_rows), ptr(z),
+               C.c_uint32(log_blowup), C.c_uint32(num_queries), C.c_uint32(pow_bits), C.c_uint32(batch_pow_bits),
+               ptr(rw) if rw is not None else None, ptr(challenger.st), ptr(commits), ptr(claims), ptr(proof),
+               C.c_uint64(cap))
+    if nwords < 0:
+        raise RuntimeError(f"oracle jagged_prove_verify failed ({nwords})")
+    return commits, claims, proof[:nwords].copy()
+
+
+def random_tables(rng, shapes):
+    """shapes: list of (rows, cols) -> list of [cols, rows] Montgomery arrays"""
+    return [rand_field(rng, (c, r)) if r else np.zeros((c, 0), np.uint32) for r, c in shapes]

@@ -210,3 +210,27 @@ def test_stacked_basefold_roundtrip(ncols, log_h):
     commits2, proof2 = O.stacked_prove_verify(rounds, log_h, point, ch2, num_queries=10, pow_bits=6, batch_pow_bits=3,
                                               replay=[batch_w, pow_w])
     assert (proof == proof2).all() and (commits == commits2).all() and (ch1.st == ch2.st).all()
+
+
+@pytest.mark.parametrize("shapes_rounds,log_stack,max_log_rows", [
+    ([[(5, 3), (0, 2), (8, 1)]], 3, 3),                       # one round, an empty table, a full-height table
+    ([[(3, 2), (7, 1)], [(16, 2), (0, 4), (9, 3)]], 3, 4),    # preprocessed + main rounds
+    ([[(1, 1)]], 2, 2),                                        # tiny: padding dominates
+    ([[(32, 5), (17, 3)], [(20, 7)]], 4, 5),
+])
+def test_jagged_pcs_roundtrip(shapes_rounds, log_stack, max_log_rows):
+    """jagged commit + Hadamard sumcheck + branching-program sumcheck + stacked/BaseFold proof -> restated
+    JaggedPcsVerifier accepts (inside the oracle call); replay reproduces the proof."""
+    rng = np.random.default_rng(31)
+    rounds = [O.random_tables(rng, s) for s in shapes_rounds]
+    z_row = O.rand_field(rng, (max_log_rows, 4))
+    ch = O.Challenger()
+    ch.observe(O.rand_field(rng, 3))
+    c1 = ch.clone()
+    commits, claims, proof = O.jagged_prove_verify(rounds, log_stack, max_log_rows, z_row, c1, num_queries=8, pow_bits=4,
+                                                   batch_pow_bits=2)
+    assert proof.size > 100 and claims.shape[0] == sum(c for s in shapes_rounds for _, c in s)
+    c2 = ch.clone()
+    commits2, claims2, proof2 = O.jagged_prove_verify(rounds, log_stack, max_log_rows, z_row, c2, num_queries=8, pow_bits=4,
+                                                      batch_pow_bits=2)
+    assert (proof == proof2).all() and (c1.st == c2.st).all() and (commits == commits2).all()

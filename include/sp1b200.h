@@ -124,6 +124,38 @@ sp1b200_err sp1b200_stacked_prove(sp1b200_ctx* ctx, sp1b200_commit* const* round
                                   uint32_t* h_challenger34, uint32_t* h_proof, uint64_t proof_cap_words,
                                   uint64_t* h_proof_words);
 
+/* ---- jagged PCS (replaces sp1-gpu/crates/{jagged_sumcheck,jagged_assist} + the jagged part of shard_prover) -------- */
+
+typedef struct sp1b200_jagged_round sp1b200_jagged_round; /* one commitment round: tables, dense buffer, stacked data */
+
+/* JaggedProver::commit_multilinears (slop/crates/jagged/src/prover.rs:106-160) for one round of chip tables.
+ * dense_any: the tables' real cells back to back in table order, each table column-major [cols x rows]
+ * (tables with rows == 0 contribute no data but do enter the row/column counts), host or device memory; this is the
+ * reference's TraceDenseData layout (sp1-gpu/crates/utils/src/traces.rs:48-75).  The library keeps its own copy,
+ * zero-padded to a multiple of 2^log_stacking_height, appends the two dummy tables to the counts and returns
+ * commit = compress(stacked_commit, hash(n, rows.., cols..)). */
+sp1b200_err sp1b200_jagged_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, uint32_t n_tables, const uint64_t* h_rows,
+                                  const uint64_t* h_cols, int keep_codeword, uint32_t* h_commit8, sp1b200_jagged_round** out);
+void sp1b200_jagged_round_free(sp1b200_ctx* ctx, sp1b200_jagged_round* round);
+
+/* Evaluations at z_row (max_log_row_count ext elements) of every table column of the round, zero-extended to
+ * 2^max_log_row_count rows: the per-column claims zerocheck hands to the PCS
+ * (crates/hypercube/src/prover/shard.rs:736-767).  h_out: sum(cols) ext elements in table/column order. */
+sp1b200_err sp1b200_jagged_column_claims(sp1b200_ctx* ctx, const sp1b200_jagged_round* round, const uint32_t* h_z_row,
+                                         uint32_t* h_out);
+
+/* JaggedProver::prove_trusted_evaluations (slop/crates/jagged/src/prover.rs:162-328): sample z_col, Hadamard sumcheck
+ * of the dense trace against the jagged little polynomial, branching-program evaluation sumcheck, stacked/BaseFold
+ * proof at the sumcheck point.  h_claims: per round, that round's column claims back to back (ext each).
+ * Proof words (field order of JaggedPcsProof, slop/crates/jagged/src/verifier.rs:17-27):
+ *   stacked proof (see sp1b200_stacked_prove) | sumcheck {n_polys, per poly {n_coeffs, coeffs ext}, claimed_sum ext,
+ *   point ext[n_polys], eval ext} | jagged_eval (same layout) | per round {n_tables, (rows, cols) per table} |
+ *   original commitments digest[n_rounds] | expected_eval ext | max_log_row_count | log_m */
+sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* rounds, uint32_t n_rounds,
+                                 const uint32_t* h_z_row, const uint32_t* h_claims, const uint32_t* h_replay_witnesses,
+                                 uint32_t* h_challenger34, uint32_t* h_proof, uint64_t proof_cap_words,
+                                 uint64_t* h_proof_words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,7 +74,7 @@ sp1b200_err sp1b200_grind_device(sp1b200_ctx* ctx, uint32_t* d_state, uint32_t b
 
 // ---- host challenger -----------------------------------------------------------------------------------------
 namespace {
-constexpr p2::RcTable RC_HOST = p2::make_rc();
+using p2::RC_HOST;
 inline uint32_t h_reduce(uint64_t x) {
     uint32_t m = (uint32_t)x * kb::MPRIME;
     uint64_t u = x + (uint64_t)m * kb::P;

@@ -1,0 +1,632 @@
+// Jagged PCS on the device: commit of a round of chip tables and the evaluation proof
+// (Hadamard sumcheck of the dense trace against the jagged "little polynomial", the branching-program
+// evaluation sumcheck, then the stacked/BaseFold proof of pcs.cu).
+// Reference behaviour: slop/crates/jagged/src/prover.rs:106-328, hadamard.rs:93-151, poly.rs:136-296,384-470,
+// jagged_eval/{sumcheck_poly.rs,sumcheck_sum_as_poly.rs,eval_sumcheck_prover.rs}; the GPU twins it replaces:
+// sp1-gpu/crates/{jagged_sumcheck,jagged_assist} + sys/lib/{jagged_sumcheck,jagged_assist}/*.cu.
+// HOW (results identical): the dense buffers of all rounds form one virtual long vector (no restacking copy);
+// each sumcheck round after the first runs as ONE fused kernel (fix the previous variable + accumulate the next
+// round's sums) so the folded vectors are written once and read once; the branching-program sumcheck evaluates all
+// (column, node) pairs of a round in one launch.
+#include "ctx.cuh"
+#include "challenger.cuh"
+#include "hostfield.hpp"
+#include "kb31.cuh"
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+struct sp1b200_commit;
+extern "C" sp1b200_err sp1b200_stacked_commit(sp1b200_ctx*, const uint32_t*, uint64_t, int, uint32_t*, sp1b200_commit**);
+extern "C" void sp1b200_commit_free(sp1b200_ctx*, sp1b200_commit*);
+extern "C" sp1b200_err sp1b200_stacked_prove(sp1b200_ctx*, sp1b200_commit* const*, uint32_t, const uint32_t*, uint32_t, const uint32_t*,
+                                             uint32_t*, uint32_t*, uint64_t, uint64_t*);
+void host_poseidon2_permute(uint32_t* s16);
+
+struct sp1b200_jagged_round {
+    sp1b200_commit* stacked = nullptr;
+    std::vector<uint64_t> row_counts, col_counts;  // including the two dummy tables
+    uint64_t padding_cols = 0, area = 0, padded_area = 0;
+    uint32_t* d_dense = nullptr;  // owned, padded_area words
+    uint32_t original_commit[8], commit[8];
+};
+
+namespace {
+
+using kb::Ext;
+using hf::E4;
+
+// ---- host sponge (PaddingFreeSponge) for the table-shape hash; a few dozen words ----------------------------------
+void host_hash(const std::vector<uint32_t>& w, uint32_t* out8) {
+    uint32_t st[16] = {0};
+    size_t i = 0;
+    while (i < w.size()) {
+        size_t k = std::min<size_t>(8, w.size() - i);
+        for (size_t j = 0; j < k; j++) st[j] = w[i + j];
+        host_poseidon2_permute(st);
+        i += k;
+    }
+    for (int j = 0; j < 8; j++) out8[j] = st[j];
+}
+void host_compress(const uint32_t* l, const uint32_t* r, uint32_t* out8) {
+    uint32_t st[16];
+    for (int j = 0; j < 8; j++) { st[j] = l[j]; st[8 + j] = r[j]; }
+    host_poseidon2_permute(st);
+    for (int j = 0; j < 8; j++) out8[j] = st[j];
+}
+
+struct DevFree {
+    sp1b200_ctx* ctx;
+    std::vector<void*> ptrs;
+    explicit DevFree(sp1b200_ctx* c) : ctx(c) {}
+    ~DevFree() { for (void* p : ptrs) cudaFreeAsync(p, ctx->stream); }
+    sp1b200_err alloc(void** p, size_t bytes) {
+        SP1_CUDA(cudaMallocAsync(p, bytes ? bytes : 4, ctx->stream));
+        ptrs.push_back(*p);
+        return nullptr;
+    }
+};
+inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+// E[j] = prod_t (j_t ? x_t : 1 - x_t), point[0] <-> MSB of j
+__global__ void eq_table_kernel(const uint32_t* __restrict__ point, int k, uint32_t* __restrict__ E) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ((uint64_t)1 << k)) return;
+    Ext acc = kb::ext_one();
+    for (int t = 0; t < k; t++) {
+        Ext x = kb::ext_load(point + 4 * t);
+        bool bit = (j >> (k - 1 - t)) & 1;
+        acc = kb::ext_mul(acc, bit ? x : kb::ext_sub(kb::ext_one(), x));
+    }
+    kb::ext_store(E + 4 * j, acc);
+}
+
+// per-column claims: out[c] = sum_{r < rows} row_eq[r] * col[r]   (one block per column)
+__global__ void __launch_bounds__(256) column_claims_kernel(const uint32_t* __restrict__ dense, const uint64_t* __restrict__ col_start,
+                                                            const uint64_t* __restrict__ col_rows, const uint32_t* __restrict__ row_eq,
+                                                            uint32_t* __restrict__ out) {
+    const uint64_t c = blockIdx.x;
+    const uint32_t* col = dense + col_start[c];
+    const uint64_t rows = col_rows[c];
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (uint64_t i = threadIdx.x; i < rows; i += blockDim.x) {
+        uint32_t x = __ldg(col + i);
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(row_eq + 4 * i));
+        a0 = kb::add(a0, kb::mul(x, v.x)); a1 = kb::add(a1, kb::mul(x, v.y));
+        a2 = kb::add(a2, kb::mul(x, v.z)); a3 = kb::add(a3, kb::mul(x, v.w));
+    }
+    __shared__ uint32_t red[4][256];
+    red[0][threadIdx.x] = a0; red[1][threadIdx.x] = a1; red[2][threadIdx.x] = a2; red[3][threadIdx.x] = a3;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+            for (int l = 0; l < 4; l++) red[l][threadIdx.x] = kb::add(red[l][threadIdx.x], red[l][threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) out[c * 4 + threadIdx.x] = red[threadIdx.x][0];
+}
+
+// jagged little polynomial: ext[i] = col_eq[c(i)] * row_eq[i - prefix[c(i)]] for i < prefix[ncols], else 0
+__global__ void __launch_bounds__(256) jagged_poly_kernel(const uint64_t* __restrict__ prefix, uint32_t ncols, const uint32_t* __restrict__ col_eq,
+                                                          const uint32_t* __restrict__ row_eq, uint64_t N, uint32_t* __restrict__ ext) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    Ext v = kb::ext_zero();
+    if (i < prefix[ncols]) {
+        // largest c with prefix[c] <= i  (zero-height columns share a prefix value: take the last, whose range is non-empty)
+        uint32_t lo = 0, hi = ncols;  // invariant prefix[lo] <= i < prefix[hi]
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (prefix[mid] <= i) lo = mid; else hi = mid; }
+        v = kb::ext_mul(kb::ext_load(col_eq + 4 * lo), kb::ext_load(row_eq + 4 * (i - prefix[lo])));
+    }
+    kb::ext_store(ext + 4 * i, v);
+}
+
+struct SegTable {  // the virtual long base vector = concatenation of the rounds' dense buffers, then zeros
+    const uint32_t* ptr[8];
+    uint64_t end[8];
+    int n;
+};
+__device__ __forceinline__ uint32_t seg_load(const SegTable& t, uint64_t i) {
+    uint64_t start = 0;
+#pragma unroll 1
+    for (int s = 0; s < t.n; s++) { if (i < t.end[s]) return __ldg(t.ptr[s] + (i - start)); start = t.end[s]; }
+    return 0;
+}
+
+__device__ __forceinline__ void block_reduce2(Ext a, Ext b, uint32_t* __restrict__ partial) {
+    __shared__ uint32_t red[8][256];
+    for (int l = 0; l < 4; l++) { red[l][threadIdx.x] = a.c[l]; red[4 + l][threadIdx.x] = b.c[l]; }
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+            for (int l = 0; l < 8; l++) red[l][threadIdx.x] = kb::add(red[l][threadIdx.x], red[l][threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x < 8) partial[blockIdx.x * 8 + threadIdx.x] = red[threadIdx.x][0];
+}
+
+// round 0: sum_j ext[2j]*base[2j]  and  sum_j (ext[2j]+ext[2j+1]) * (base[2j]+base[2j+1])   (base in F)
+__global__ void __launch_bounds__(256) hadamard_sum0_kernel(SegTable base, const uint32_t* __restrict__ ext, uint64_t npairs,
+                                                            uint32_t* __restrict__ partial) {
+    Ext s0 = kb::ext_zero(), sh = kb::ext_zero();
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < npairs; j += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t b0 = seg_load(base, 2 * j), b1 = seg_load(base, 2 * j + 1);
+        Ext e0 = kb::ext_load(ext + 8 * j), e1 = kb::ext_load(ext + 8 * j + 4);
+        s0 = kb::ext_add(s0, kb::ext_mul_base(e0, b0));
+        sh = kb::ext_add(sh, kb::ext_mul_base(kb::ext_add(e0, e1), kb::add(b0, b1)));
+    }
+    block_reduce2(s0, sh, partial);
+}
+
+// fix the last variable of round 0 (base F -> EF) and accumulate round-1 sums
+__global__ void __launch_bounds__(256) hadamard_fold0_kernel(SegTable base, const uint32_t* __restrict__ ext, uint64_t nout_pairs, Ext alpha,
+                                                             uint32_t* __restrict__ base_out, uint32_t* __restrict__ ext_out,
+                                                             uint32_t* __restrict__ partial, uint64_t nout) {
+    Ext s0 = kb::ext_zero(), sh = kb::ext_zero();
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nout_pairs; j += (uint64_t)gridDim.x * blockDim.x) {
+        Ext nb[2], ne[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint64_t o = 2 * j + h;  // output index; inputs 2o, 2o+1
+            if (o < nout) {
+                uint32_t b0 = seg_load(base, 2 * o), b1 = seg_load(base, 2 * o + 1);
+                Ext e0 = kb::ext_load(ext + 8 * o), e1 = kb::ext_load(ext + 8 * o + 4);
+                nb[h] = kb::ext_add(kb::ext_from_base(b0), kb::ext_mul_base(alpha, kb::sub(b1, b0)));
+                ne[h] = kb::ext_add(e0, kb::ext_mul(alpha, kb::ext_sub(e1, e0)));
+                kb::ext_store(base_out + 4 * o, nb[h]);
+                kb::ext_store(ext_out + 4 * o, ne[h]);
+            } else { nb[h] = kb::ext_zero(); ne[h] = kb::ext_zero(); }
+        }
+        s0 = kb::ext_add(s0, kb::ext_mul(ne[0], nb[0]));
+        sh = kb::ext_add(sh, kb::ext_mul(kb::ext_add(ne[0], ne[1]), kb::ext_add(nb[0], nb[1])));
+    }
+    block_reduce2(s0, sh, partial);
+}
+
+// rounds >= 1: fix the last variable (EF -> EF) and accumulate the next round's sums
+__global__ void __launch_bounds__(256) hadamard_fold_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ ext,
+                                                            uint64_t nout_pairs, Ext alpha, uint32_t* __restrict__ base_out,
+                                                            uint32_t* __restrict__ ext_out, uint32_t* __restrict__ partial, uint64_t nout) {
+    Ext s0 = kb::ext_zero(), sh = kb::ext_zero();
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nout_pairs; j += (uint64_t)gridDim.x * blockDim.x) {
+        Ext nb[2], ne[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint64_t o = 2 * j + h;
+            if (o < nout) {
+                Ext b0 = kb::ext_load(base + 8 * o), b1 = kb::ext_load(base + 8 * o + 4);
+                Ext e0 = kb::ext_load(ext + 8 * o), e1 = kb::ext_load(ext + 8 * o + 4);
+                nb[h] = kb::ext_add(b0, kb::ext_mul(alpha, kb::ext_sub(b1, b0)));
+                ne[h] = kb::ext_add(e0, kb::ext_mul(alpha, kb::ext_sub(e1, e0)));
+                kb::ext_store(base_out + 4 * o, nb[h]);
+                kb::ext_store(ext_out + 4 * o, ne[h]);
+            } else { nb[h] = kb::ext_zero(); ne[h] = kb::ext_zero(); }
+        }
+        s0 = kb::ext_add(s0, kb::ext_mul(ne[0], nb[0]));
+        sh = kb::ext_add(sh, kb::ext_mul(kb::ext_add(ne[0], ne[1]), kb::ext_add(nb[0], nb[1])));
+    }
+    block_reduce2(s0, sh, partial);
+}
+
+// ---- branching program (slop/crates/jagged/src/poly.rs:136-175, 384-470) ---------------------------------------
+// state index = carry + 2 * comparison_so_far ; returns -1 on failure
+__device__ __forceinline__ int bp_transition(int row_bit, int index_bit, int cur_bit, int next_bit, int state) {
+    int carry = state & 1, cmp = state >> 1;
+    int new_cmp = (index_bit == next_bit) ? cmp : next_bit;
+    int s = row_bit + carry + cur_bit;
+    if (index_bit != (s & 1)) return -1;
+    return (s >> 1) + 2 * new_cmp;
+}
+
+// One thread per (merged prefix sum k, node in {0, 1/2}).  Point of thread (k, node), big-endian, length dim = 2*(lm+1):
+//   [ bits[k][0 .. split) , lambda , rhos[0 .. round) ]   with split = dim - round - 1
+// left half = "prefix_sum", right half = "next_prefix_sum"; layer l reads the l-th least significant coordinate of each.
+// ri_eq: per layer the 4 values eq((z_row_l, z_index_l), (a, b)) for (a,b) = 00,01,10,11  (shared by all threads).
+// has_lambda == 0: the point is the boolean prefix sums themselves (split == dim): full evaluation, weight zc only.
+__global__ void __launch_bounds__(128) bp_round_kernel(const uint8_t* __restrict__ bits, uint32_t nk, uint32_t dim, uint32_t split,
+                                                       int has_lambda, const uint32_t* __restrict__ rhos, const uint32_t* __restrict__ ri_eq,
+                                                       const uint32_t* __restrict__ zc, const uint32_t* __restrict__ inter, Ext half,
+                                                       uint32_t* __restrict__ partial) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    Ext v = kb::ext_zero();
+    const uint32_t k = t >> 1, node = t & 1;
+    const uint32_t hl = dim / 2;  // lm + 1
+    if (k < nk && (has_lambda || node == 0)) {
+        const uint8_t* b = bits + (size_t)k * dim;
+        auto coord = [&](uint32_t pos) -> Ext {  // pos in [0, dim)
+            if (pos < split) return b[pos] ? kb::ext_one() : kb::ext_zero();
+            if (has_lambda && pos == split) return node ? half : kb::ext_zero();
+            return kb::ext_load(rhos + 4 * (pos - split - 1));
+        };
+        Ext res[4] = {kb::ext_zero(), kb::ext_zero(), kb::ext_one(), kb::ext_zero()};  // success = carry 0, cmp 1
+        for (int layer = (int)hl; layer >= 0; layer--) {
+            // num_vars = hl (z_index has lm+1 coordinates); layer == hl reads beyond every point -> all coordinates 0
+            Ext cur = kb::ext_zero(), nxt = kb::ext_zero();
+            Ext r00 = kb::ext_one(), r01 = kb::ext_zero(), r10 = kb::ext_zero(), r11 = kb::ext_zero();
+            if ((uint32_t)layer < hl) {
+                cur = coord(hl - 1 - layer);
+                nxt = coord(dim - 1 - layer);
+                const uint32_t* e = ri_eq + (size_t)layer * 16;
+                r00 = kb::ext_load(e); r01 = kb::ext_load(e + 4); r10 = kb::ext_load(e + 8); r11 = kb::ext_load(e + 12);
+            }
+            // eq over (cur, next): c00, c01, c10, c11
+            Ext cn = kb::ext_mul(cur, nxt);
+            Ext c11 = cn, c10 = kb::ext_sub(cur, cn), c01 = kb::ext_sub(nxt, cn);
+            Ext c00 = kb::ext_sub(kb::ext_sub(kb::ext_one(), cur), c01);
+            const Ext ri[4] = {r00, r01, r10, r11};
+            const Ext cc[4] = {c00, c01, c10, c11};
+            Ext nres[4];
+#pragma unroll
+            for (int st = 0; st < 4; st++) {
+                Ext acc = kb::ext_zero();
+#pragma unroll
+                for (int a = 0; a < 4; a++) {      // (row_bit, index_bit)
+                    Ext inner = kb::ext_zero();
+                    bool any = false;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {  // (cur_bit, next_bit)
+                        int o = bp_transition(a >> 1, a & 1, c >> 1, c & 1, st);
+                        if (o >= 0) { inner = kb::ext_add(inner, kb::ext_mul(cc[c], res[o])); any = true; }
+                    }
+                    if (any) acc = kb::ext_add(acc, kb::ext_mul(ri[a], inner));
+                }
+                nres[st] = acc;
+            }
+#pragma unroll
+            for (int st = 0; st < 4; st++) res[st] = nres[st];
+        }
+        // eq factor of this round's variable and the accumulated one
+        v = kb::ext_mul(kb::ext_load(zc + 4 * k), res[0]);
+        if (has_lambda) {
+            Ext eqv = node ? half : (b[split] ? kb::ext_zero() : kb::ext_one());
+            v = kb::ext_mul(v, kb::ext_mul(kb::ext_load(inter + 4 * k), eqv));
+        }
+    }
+    // block reduce: node 0 -> y_0, node 1 -> y_half
+    __shared__ uint32_t red[4][128];
+    for (int l = 0; l < 4; l++) red[l][threadIdx.x] = v.c[l];
+    __syncthreads();
+    for (int s = 64; s >= 2; s >>= 1) {  // keep parity (node) separate: stop at 2
+        if ((int)threadIdx.x < s)
+            for (int l = 0; l < 4; l++) red[l][threadIdx.x] = kb::add(red[l][threadIdx.x], red[l][threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x < 8) partial[blockIdx.x * 8 + threadIdx.x] = red[threadIdx.x & 3][threadIdx.x >> 2];
+}
+
+// inter[k] *= alpha * x + (1 - alpha) * (1 - x),  x = bits[k][dim - 1 - round]
+__global__ void bp_fix_kernel(const uint8_t* __restrict__ bits, uint32_t nk, uint32_t dim, uint32_t round, Ext alpha, uint32_t* __restrict__ inter) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nk) return;
+    Ext f = bits[(size_t)k * dim + dim - 1 - round] ? alpha : kb::ext_sub(kb::ext_one(), alpha);
+    kb::ext_store(inter + 4 * k, kb::ext_mul(kb::ext_load(inter + 4 * k), f));
+}
+
+// p(x) through (0, y0), (1, y1), (1/2, yh): coefficients c0, c1, c2
+inline void interp_0_1_half(const E4& y0, const E4& y1, const E4& yh, E4 c[3]) {
+    const uint32_t two = hf::to_monty(2), three = hf::to_monty(3), four = hf::to_monty(4);
+    c[0] = y0;
+    c[1] = yh * four - y0 * three - y1;
+    c[2] = (y1 + y0) * two - yh * four;
+}
+inline E4 eval3(const E4 c[3], const E4& x) { return (c[2] * x + c[1]) * x + c[0]; }
+
+sp1b200_err sum_partials(sp1b200_ctx* ctx, const uint32_t* d_partial, unsigned nblk, E4& a, E4& b) {
+    std::vector<uint32_t> h((size_t)nblk * 8);
+    SP1_CUDA(cudaMemcpyAsync(h.data(), d_partial, h.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SP1_CUDA(cudaStreamSynchronize(ctx->stream));
+    a = E4(); b = E4();
+    for (unsigned k = 0; k < nblk; k++) { a = a + E4::load(&h[8 * k]); b = b + E4::load(&h[8 * k + 4]); }
+    return nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Jagged commit of one round of chip tables (slop/crates/jagged/src/prover.rs:106-160).
+// dense_any: the tables' real cells back to back, each table column-major [cols x rows] (tables with 0 rows
+// contribute nothing), host or device; the library keeps its own zero-padded device copy.
+sp1b200_err sp1b200_jagged_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, uint32_t n_tables, const uint64_t* rows, const uint64_t* cols,
+                                  int keep_codeword, uint32_t* h_commit8, sp1b200_jagged_round** out) {
+    const uint32_t ls = ctx->params.log_stacking_height, mlr = ctx->params.max_log_row_count;
+    auto r = std::make_unique<sp1b200_jagged_round>();
+    uint64_t area = 0;
+    for (uint32_t t = 0; t < n_tables; t++) {
+        if (rows[t] > ((uint64_t)1 << mlr)) return sp1b200_set_error("jagged_commit: table %u has %llu rows > 2^%u", t, (unsigned long long)rows[t], mlr);
+        r->row_counts.push_back(rows[t]); r->col_counts.push_back(cols[t]); area += rows[t] * cols[t];
+    }
+    const uint64_t S = (uint64_t)1 << ls, R = (uint64_t)1 << mlr;
+    const uint64_t padded = std::max(((area + S - 1) / S) * S, S);
+    const uint64_t added = padded - area;
+    r->area = area; r->padded_area = padded;
+    SP1_CUDA(cudaMallocAsync((void**)&r->d_dense, padded * 4, ctx->stream));
+    if (area) SP1_CUDA(cudaMemcpyAsync(r->d_dense, dense_any, area * 4, cudaMemcpyDefault, ctx->stream));
+    if (added) SP1_CUDA(cudaMemsetAsync(r->d_dense + area, 0, added * 4, ctx->stream));
+    sp1b200_err e = sp1b200_stacked_commit(ctx, r->d_dense, padded / S, keep_codeword, r->original_commit, &r->stacked);
+    if (e) { cudaFreeAsync(r->d_dense, ctx->stream); return e; }
+    const uint64_t added_cols = std::max<uint64_t>((added + R - 1) / R, 1);
+    r->row_counts.push_back(R); r->row_counts.push_back(added - (added_cols - 1) * R);
+    r->col_counts.push_back(added_cols - 1); r->col_counts.push_back(1);
+    r->padding_cols = added_cols;
+    std::vector<uint32_t> meta{hf::to_monty(r->row_counts.size())};
+    for (uint64_t x : r->row_counts) meta.push_back(hf::to_monty(x));
+    for (uint64_t x : r->col_counts) meta.push_back(hf::to_monty(x));
+    uint32_t hsh[8];
+    host_hash(meta, hsh);
+    host_compress(r->original_commit, hsh, r->commit);
+    if (h_commit8) memcpy(h_commit8, r->commit, 32);
+    *out = r.release();
+    return nullptr;
+}
+
+void sp1b200_jagged_round_free(sp1b200_ctx* ctx, sp1b200_jagged_round* r) {
+    if (!r) return;
+    sp1b200_commit_free(ctx, r->stacked);
+    if (r->d_dense) cudaFreeAsync(r->d_dense, ctx->stream);
+    delete r;
+}
+
+// Per-column evaluations of every table column of the round at z_row (zero-padded to 2^max_log_row_count rows):
+// the claims zerocheck hands to the PCS (crates/hypercube/src/prover/shard.rs:736-767).  h_out: sum(cols) ext elements.
+sp1b200_err sp1b200_jagged_column_claims(sp1b200_ctx* ctx, const sp1b200_jagged_round* r, const uint32_t* h_z_row, uint32_t* h_out) {
+    const uint32_t mlr = ctx->params.max_log_row_count;
+    DevFree mem(ctx);
+    uint32_t *d_z, *d_eq, *d_out;
+    uint64_t *d_start, *d_rows;
+    std::vector<uint64_t> start, nrows;
+    uint64_t off = 0;
+    for (size_t t = 0; t + 2 < r->row_counts.size(); t++)
+        for (uint64_t c = 0; c < r->col_counts[t]; c++) { start.push_back(off); nrows.push_back(r->row_counts[t]); off += r->row_counts[t]; }
+    const size_t nc = start.size();
+    if (!nc) return nullptr;
+    SP1_TRY(mem.alloc((void**)&d_z, mlr * 16));
+    SP1_TRY(mem.alloc((void**)&d_eq, ((size_t)16) << mlr));
+    SP1_TRY(mem.alloc((void**)&d_out, nc * 16));
+    SP1_TRY(mem.alloc((void**)&d_start, nc * 8));
+    SP1_TRY(mem.alloc((void**)&d_rows, nc * 8));
+    SP1_CUDA(cudaMemcpyAsync(d_z, h_z_row, mlr * 16, cudaMemcpyHostToDevice, ctx->stream));
+    SP1_CUDA(cudaMemcpyAsync(d_start, start.data(), nc * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SP1_CUDA(cudaMemcpyAsync(d_rows, nrows.data(), nc * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SP1_LAUNCH(ctx, eq_table_kernel, blocks_for((uint64_t)1 << mlr), 256, 0, d_z, (int)mlr, d_eq);
+    SP1_LAUNCH(ctx, column_claims_kernel, (unsigned)nc, 256, 0, r->d_dense, d_start, d_rows, d_eq, d_out);
+    SP1_CUDA(cudaMemcpyAsync(h_out, d_out, nc * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SP1_CUDA(cudaStreamSynchronize(ctx->stream));
+    return nullptr;
+}
+
+// JaggedProver::prove_trusted_evaluations (slop/crates/jagged/src/prover.rs:162-328).
+// h_claims: for each round, the evaluations at z_row of that round's table columns (ext each), back to back.
+// Proof words: stacked proof | sumcheck {n_polys, per poly {n_coeffs, coeffs}, claimed_sum, point, eval} |
+// jagged_eval (same layout) | per round {n_tables, (rows, cols)...} | original commitments | expected_eval |
+// max_log_row_count | log_m        (field order of JaggedPcsProof, slop/crates/jagged/src/verifier.rs:17-27)
+sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* rounds, uint32_t n_rounds, const uint32_t* h_z_row,
+                                 const uint32_t* h_claims, const uint32_t* h_replay, uint32_t* h_chal, uint32_t* h_proof, uint64_t cap,
+                                 uint64_t* h_words) {
+    if (!n_rounds || n_rounds > 8) return sp1b200_set_error("jagged_prove: 1..8 rounds supported");
+    const uint32_t mlr = ctx->params.max_log_row_count, ls = ctx->params.log_stacking_height;
+    cudaStream_t st = ctx->stream;
+    DevFree mem(ctx);
+    HostChallenger ch;
+    SP1_TRY(ch.init(ctx, h_chal));
+    PhaseTimer t_all(ctx, "jagged.total");
+
+    // column heights over all rounds (dummy tables included) and prefix sums
+    std::vector<uint64_t> heights;
+    uint64_t total_cols = 0;
+    for (uint32_t r = 0; r < n_rounds; r++)
+        for (size_t t = 0; t < rounds[r]->row_counts.size(); t++)
+            for (uint64_t c = 0; c < rounds[r]->col_counts[t]; c++) { heights.push_back(rounds[r]->row_counts[t]); total_cols++; }
+    std::vector<uint64_t> prefix;
+    { uint64_t s = 0; for (uint64_t hgt : heights) { prefix.push_back(s); s += hgt; } prefix.push_back(prefix.back() + heights.back()); }
+    const uint32_t lm = hf::log2_ceil(prefix.back());
+    if (lm < ls) return sp1b200_set_error("jagged_prove: internal: log_m < log_stacking_height");
+    const uint64_t N = (uint64_t)1 << lm;
+    const uint32_t ncv = hf::log2_ceil(total_cols);
+    std::vector<E4> z_col(ncv), z_row(mlr);
+    for (auto& x : z_col) ch.sample_ext(x.c);
+    for (uint32_t i = 0; i < mlr; i++) z_row[i] = E4::load(h_z_row + 4 * i);
+
+    // column claims with zeros for the padding columns; sumcheck claim = MLE(column_claims)(z_col)
+    std::vector<E4> column_claims;
+    {
+        size_t k = 0;
+        for (uint32_t r = 0; r < n_rounds; r++) {
+            uint64_t real = 0;
+            for (size_t t = 0; t + 2 < rounds[r]->col_counts.size(); t++) real += rounds[r]->col_counts[t];
+            for (uint64_t c = 0; c < real; c++) column_claims.push_back(E4::load(h_claims + 4 * (k++)));
+            for (uint64_t c = 0; c < rounds[r]->padding_cols; c++) column_claims.push_back(E4());
+        }
+    }
+    std::vector<E4> col_eq_full = hf::partial_lagrange(z_col);
+    E4 claim;
+    for (size_t i = 0; i < column_claims.size(); i++) claim = claim + col_eq_full[i] * column_claims[i];
+
+    // device tables: col_eq (over last log2_ceil(ncols) coords of z_col == all of z_col), row_eq, prefix sums
+    uint32_t *d_coleq, *d_zrow, *d_roweq, *d_ext, *d_ext2, *d_b, *d_b2, *d_partial;
+    uint64_t* d_prefix;
+    SP1_TRY(mem.alloc((void**)&d_coleq, col_eq_full.size() * 16));
+    SP1_CUDA(cudaMemcpyAsync(d_coleq, col_eq_full.data(), col_eq_full.size() * 16, cudaMemcpyHostToDevice, st));
+    SP1_TRY(mem.alloc((void**)&d_zrow, mlr * 16));
+    SP1_CUDA(cudaMemcpyAsync(d_zrow, h_z_row, mlr * 16, cudaMemcpyHostToDevice, st));
+    SP1_TRY(mem.alloc((void**)&d_roweq, ((size_t)16) << mlr));
+    SP1_LAUNCH(ctx, eq_table_kernel, blocks_for((uint64_t)1 << mlr), 256, 0, d_zrow, (int)mlr, d_roweq);
+    SP1_TRY(mem.alloc((void**)&d_prefix, prefix.size() * 8));
+    SP1_CUDA(cudaMemcpyAsync(d_prefix, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice, st));
+    SP1_TRY(mem.alloc((void**)&d_ext, N * 16));
+    SP1_TRY(mem.alloc((void**)&d_ext2, (N / 2) * 16));
+    SP1_TRY(mem.alloc((void**)&d_b, (N / 2) * 16));
+    SP1_TRY(mem.alloc((void**)&d_b2, (N / 4 + 1) * 16));
+    const unsigned MAXB = 148 * 8;
+    SP1_TRY(mem.alloc((void**)&d_partial, (size_t)MAXB * 32 + 4096));
+    {
+        PhaseTimer t(ctx, "jagged.little_poly");
+        SP1_LAUNCH(ctx, jagged_poly_kernel, blocks_for(N), 256, 0, d_prefix, (uint32_t)total_cols, d_coleq, d_roweq, N, d_ext);
+        t.stop();
+    }
+    SegTable seg{};
+    seg.n = (int)n_rounds;
+    { uint64_t e = 0; for (uint32_t r = 0; r < n_rounds; r++) { seg.ptr[r] = rounds[r]->d_dense; e += rounds[r]->padded_area; seg.end[r] = e; } }
+
+    // ---- Hadamard sumcheck (lambda = 1, t = 1) ---------------------------------------------------------------------
+    std::vector<uint32_t> sc_words;     // univariate polys
+    std::vector<E4> point;              // most recent challenge first
+    E4 round_claim = claim;
+    PhaseTimer t_sc(ctx, "jagged.sumcheck");
+    auto grid_for = [&](uint64_t n) { unsigned g = blocks_for(n); return g > MAXB ? MAXB : (g ? g : 1u); };
+    uint32_t *cur_b = nullptr, *cur_e = d_ext, *nxt_b = d_b, *nxt_e = d_ext2;
+    unsigned prev_g = 0;
+    for (uint32_t rd = 0; rd < lm; rd++) {
+        const uint64_t n = N >> rd;  // current length
+        E4 e0, eh;
+        unsigned g;
+        if (rd == 0) {
+            g = grid_for(n / 2);
+            SP1_LAUNCH(ctx, hadamard_sum0_kernel, g, 256, 0, seg, cur_e, n / 2, d_partial);
+            SP1_TRY(sum_partials(ctx, d_partial, g, e0, eh));
+        } else {
+            SP1_TRY(sum_partials(ctx, d_partial, prev_g, e0, eh));  // accumulated by the previous fold launch
+        }
+        E4 e1 = round_claim - e0;
+        E4 c[3];
+        interp_0_1_half(e0, e1, eh * hf::inv(hf::to_monty(4)), c);
+        for (int i = 0; i < 3; i++) ch.observe_n(c[i].c, 4);
+        uint32_t three = 3;
+        sc_words.push_back(three);
+        for (int i = 0; i < 3; i++) sc_words.insert(sc_words.end(), c[i].c, c[i].c + 4);
+        E4 alpha; ch.sample_ext(alpha.c);
+        point.insert(point.begin(), alpha);
+        round_claim = eval3(c, alpha);
+        // fix the variable; the same launch accumulates the next round's sums (unless this was the last round)
+        const uint64_t nout = n / 2;
+        Ext da{{alpha.c[0], alpha.c[1], alpha.c[2], alpha.c[3]}};
+        g = grid_for((nout + 1) / 2);
+        if (rd == 0) {
+            SP1_LAUNCH(ctx, hadamard_fold0_kernel, g, 256, 0, seg, cur_e, (nout + 1) / 2, da, nxt_b, nxt_e, d_partial, nout);
+            cur_b = nxt_b; cur_e = nxt_e; nxt_b = d_b2; nxt_e = d_ext;  // d_ext (N entries) is free again
+        } else {
+            SP1_LAUNCH(ctx, hadamard_fold_kernel, g, 256, 0, cur_b, cur_e, (nout + 1) / 2, da, nxt_b, nxt_e, d_partial, nout);
+            std::swap(cur_b, nxt_b); std::swap(cur_e, nxt_e);
+        }
+        prev_g = g;
+    }
+    // component evaluations: base[0] (the dense trace at the sumcheck point), ext[0]
+    uint32_t base_eval_w[4];
+    SP1_CUDA(cudaMemcpyAsync(base_eval_w, cur_b, 16, cudaMemcpyDeviceToHost, st));
+    SP1_CUDA(cudaStreamSynchronize(st));
+    t_sc.stop();
+    const E4 base_eval = E4::load(base_eval_w);
+
+    // ---- jagged evaluation (branching program) sumcheck --------------------------------------------------------------
+    std::vector<uint32_t> je_words;
+    std::vector<E4> rhos;
+    E4 je_claimed, je_eval;
+    {
+        PhaseTimer t(ctx, "jagged.eval_sumcheck");
+        const uint32_t dim = 2 * (lm + 1);
+        // merged prefix sums (bits), condensed over equal consecutive entries; z_col eq values summed per group
+        std::vector<uint8_t> bits;
+        std::vector<E4> zc;
+        uint32_t nk = 0;
+        for (size_t c = 0; c + 1 < prefix.size(); c++) {
+            std::vector<uint8_t> b(dim);
+            for (uint32_t i = 0; i <= lm; i++) { b[i] = (prefix[c] >> (lm - i)) & 1; b[lm + 1 + i] = (prefix[c + 1] >> (lm - i)) & 1; }
+            if (nk && std::equal(b.begin(), b.end(), bits.end() - dim)) zc.back() = zc.back() + col_eq_full[c];
+            else { bits.insert(bits.end(), b.begin(), b.end()); zc.push_back(col_eq_full[c]); nk++; }
+        }
+        // per-layer eq((z_row_l, z_index_l), .) ; z_index = the sumcheck point (lm coords), num_vars = max(mlr, lm) -> lm+1 layers used
+        const uint32_t hl = lm + 1;
+        std::vector<uint32_t> ri((size_t)hl * 16);
+        auto lsb = [](const std::vector<E4>& p, uint32_t i) { return p.size() <= i ? E4() : p[p.size() - 1 - i]; };
+        if (mlr > hl) return sp1b200_set_error("jagged_prove: max_log_row_count %u exceeds log_m+1 = %u (unsupported shape)", mlr, hl);
+        for (uint32_t l = 0; l < hl; l++) {
+            E4 zr = lsb(z_row, l), zi = lsb(point, l), one = E4::one();
+            E4 p = zr * zi;
+            E4 e11 = p, e10 = zr - p, e01 = zi - p, e00 = one - zr - e01;
+            e00.store(&ri[l * 16]); e01.store(&ri[l * 16 + 4]); e10.store(&ri[l * 16 + 8]); e11.store(&ri[l * 16 + 12]);
+        }
+        uint8_t* d_bits; uint32_t *d_ri, *d_zc, *d_inter, *d_rhos, *d_part;
+        SP1_TRY(mem.alloc((void**)&d_bits, bits.size()));
+        SP1_TRY(mem.alloc((void**)&d_ri, ri.size() * 4));
+        SP1_TRY(mem.alloc((void**)&d_zc, (size_t)nk * 16));
+        SP1_TRY(mem.alloc((void**)&d_inter, (size_t)nk * 16));
+        SP1_TRY(mem.alloc((void**)&d_rhos, (size_t)dim * 16));
+        const unsigned nblk = (2 * nk + 127) / 128;
+        SP1_TRY(mem.alloc((void**)&d_part, (size_t)nblk * 32));
+        SP1_CUDA(cudaMemcpyAsync(d_bits, bits.data(), bits.size(), cudaMemcpyHostToDevice, st));
+        SP1_CUDA(cudaMemcpyAsync(d_ri, ri.data(), ri.size() * 4, cudaMemcpyHostToDevice, st));
+        SP1_CUDA(cudaMemcpyAsync(d_zc, zc.data(), (size_t)nk * 16, cudaMemcpyHostToDevice, st));
+        std::vector<E4> ones(nk, E4::one());
+        SP1_CUDA(cudaMemcpyAsync(d_inter, ones.data(), (size_t)nk * 16, cudaMemcpyHostToDevice, st));
+        const E4 half = E4::from_base(hf::inv(hf::to_monty(2)));
+        Ext dhalf{{half.c[0], 0, 0, 0}};
+        // claimed sum = full evaluation at the boolean prefix sums (full_jagged_little_polynomial_evaluation, poly.rs:183-232)
+        E4 dummy;
+        SP1_LAUNCH(ctx, bp_round_kernel, nblk, 128, 0, d_bits, nk, dim, dim, 0, d_rhos, d_ri, d_zc, d_inter, dhalf, d_part);
+        SP1_TRY(sum_partials(ctx, d_part, nblk, je_claimed, dummy));
+        ch.observe_n(je_claimed.c, 4);
+        E4 cl = je_claimed;
+        je_words.push_back(dim);
+        for (uint32_t round = 0; round < dim; round++) {
+            if (round) SP1_CUDA(cudaMemcpyAsync(d_rhos, rhos.data(), rhos.size() * 16, cudaMemcpyHostToDevice, st));
+            SP1_LAUNCH(ctx, bp_round_kernel, nblk, 128, 0, d_bits, nk, dim, dim - round - 1, 1, d_rhos, d_ri, d_zc, d_inter, dhalf, d_part);
+            E4 y0, yh;
+            SP1_TRY(sum_partials(ctx, d_part, nblk, y0, yh));
+            E4 y1 = cl - y0;
+            E4 c[3];
+            interp_0_1_half(y0, y1, yh, c);
+            for (int i = 0; i < 3; i++) ch.observe_n(c[i].c, 4);
+            je_words.push_back(3);
+            for (int i = 0; i < 3; i++) je_words.insert(je_words.end(), c[i].c, c[i].c + 4);
+            E4 alpha; ch.sample_ext(alpha.c);
+            rhos.insert(rhos.begin(), alpha);
+            cl = eval3(c, alpha);
+            Ext da{{alpha.c[0], alpha.c[1], alpha.c[2], alpha.c[3]}};
+            SP1_LAUNCH(ctx, bp_fix_kernel, blocks_for(nk, 128), 128, 0, d_bits, nk, dim, round, da, d_inter);
+        }
+        je_eval = cl;
+        t.stop();
+    }
+
+    // ---- dense PCS: prove_untrusted_evaluation(point, base_eval) ---------------------------------------------------
+    ch.observe_n(base_eval.c, 4);
+    uint32_t chal[34];
+    ch.store(chal);
+    std::vector<sp1b200_commit*> handles;
+    for (uint32_t r = 0; r < n_rounds; r++) handles.push_back(rounds[r]->stacked);
+    std::vector<uint32_t> pt(point.size() * 4);
+    for (size_t i = 0; i < point.size(); i++) point[i].store(&pt[4 * i]);
+    std::vector<uint32_t> proof(cap ? cap : 1);
+    uint64_t nw = 0;
+    SP1_TRY(sp1b200_stacked_prove(ctx, handles.data(), n_rounds, pt.data(), (uint32_t)point.size(), h_replay, chal, proof.data(), cap, &nw));
+    proof.resize(nw);
+    auto put = [&](const uint32_t* p, size_t n) { proof.insert(proof.end(), p, p + n); };
+    auto put1 = [&](uint32_t v) { proof.push_back(v); };
+    // sumcheck proof
+    put1(lm);
+    put(sc_words.data(), sc_words.size());
+    put(claim.c, 4);
+    put(pt.data(), pt.size());
+    put(round_claim.c, 4);
+    // jagged eval proof
+    put(je_words.data(), je_words.size());
+    put(je_claimed.c, 4);
+    for (auto& x : rhos) put(x.c, 4);
+    put(je_eval.c, 4);
+    for (uint32_t r = 0; r < n_rounds; r++) {
+        put1((uint32_t)rounds[r]->row_counts.size());
+        for (size_t t = 0; t < rounds[r]->row_counts.size(); t++) { put1((uint32_t)rounds[r]->row_counts[t]); put1((uint32_t)rounds[r]->col_counts[t]); }
+    }
+    for (uint32_t r = 0; r < n_rounds; r++) put(rounds[r]->original_commit, 8);
+    put(base_eval.c, 4);
+    put1(mlr);
+    put1(lm);
+    t_all.stop();
+    memcpy(h_chal, chal, sizeof(chal));
+    if (h_words) *h_words = proof.size();
+    if (proof.size() > cap) return sp1b200_set_error("jagged_prove: proof needs %zu words, capacity %llu", proof.size(), (unsigned long long)cap);
+    if (h_proof) memcpy(h_proof, proof.data(), proof.size() * 4);
+    return nullptr;
+}
+
+}  // extern "C"

@@ -27,8 +27,14 @@ __host__ __device__ constexpr RcTable make_rc() {
 }
 
 static __constant__ RcTable RC = make_rc();
+constexpr RcTable RC_HOST = make_rc();
+#ifdef __CUDA_ARCH__
+#define P2_RC p2::RC
+#else
+#define P2_RC p2::RC_HOST
+#endif
 
-__device__ __forceinline__ void mds4(uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
+KB_HD void mds4(uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
     using namespace kb;
     uint32_t t01 = add(s0, s1), t23 = add(s2, s3);
     uint32_t t0123 = add(t01, t23);
@@ -41,7 +47,7 @@ __device__ __forceinline__ void mds4(uint32_t& s0, uint32_t& s1, uint32_t& s2, u
     s0 = n0; s1 = n1; s2 = n2; s3 = n3;
 }
 
-__device__ __forceinline__ void ext_layer(uint32_t (&s)[16]) {
+KB_HD void ext_layer(uint32_t (&s)[16]) {
     using namespace kb;
 #pragma unroll
     for (int i = 0; i < 16; i += 4) mds4(s[i], s[i + 1], s[i + 2], s[i + 3]);
@@ -55,54 +61,82 @@ __device__ __forceinline__ void ext_layer(uint32_t (&s)[16]) {
     }
 }
 
-// x^3 with x = s + rc ; returns canonical
-__device__ __forceinline__ uint32_t sbox(uint32_t s, uint32_t rc) {
-    using namespace kb;
-    uint32_t x = add(s, rc);
-    uint32_t x2 = mul_lazy(x, x);  // < 2p, fine as the left operand of the next product (x < p)
-    return mul(x2, x);
+// Montgomery product in subtraction form: t = a*b, m = t_lo * p^-1, r = t_hi - hi(m*p) in (-p, p).
+// On B200 the 32x32->64 IMAD.WIDE issues at ~1/4 and IMAD.HI at ~1/2 the rate of the 32-bit IMAD
+// (tools/pipe_bench.cu, profiles/), so every product is written as lo/hi halves and no 64-bit addend is used.
+constexpr uint32_t MU = 0x81000001u;  // +p^-1 mod 2^32
+KB_HD uint32_t mont_lazy(uint32_t a, uint32_t b) {  // result in (0, 2p), needs a*b < 2^32 p
+    uint32_t lo = a * b, hi = kb::mulhi(a, b);
+    uint32_t q = kb::mulhi(lo * MU, kb::P);
+    return hi - q + kb::P;
+}
+KB_HD uint32_t mont(uint32_t a, uint32_t b) {  // canonical
+    uint32_t lo = a * b, hi = kb::mulhi(a, b);
+    uint32_t q = kb::mulhi(lo * MU, kb::P);
+    uint32_t r = hi - q;
+    return umin(r, r + kb::P);
 }
 
-// state <- 2^-32 (J + diag(-2, 1, 2, ..., 2^13, 2^15)) state, on Montgomery words
-__device__ __forceinline__ void int_layer(uint32_t (&s)[16]) {
-    using namespace kb;
+// x^3 with x = s + rc ; canonical in, canonical out
+KB_HD uint32_t sbox(uint32_t s, uint32_t rc) {
+    uint32_t x = kb::add(s, rc);
+    uint32_t x2 = mont_lazy(x, x);  // < 1.5 p
+    return mont(x2, x);
+}
+
+// Partial-round linear layer  state <- 2^-32 (J + diag(-2, 1, 2, ..., 2^13, 2^15)) state  on Montgomery words.
+// By linearity  y_i = reduce(S) + reduce(x_i << k_i):  the shared term is reduced once, the per-lane term is a
+// shift (no multiply) followed by the two half-products of the reduction.  Lanes 1..15 are kept LAZY in
+// [0, 2p + 2^15) between partial rounds (any 32-bit x is a valid input: t_hi = x >> (32-k) < 2^15), lane 0 canonical.
+KB_HD void int_layer_lazy(uint32_t (&s)[16]) {
     uint64_t sum = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) sum += s[i];
-    // lane 0: sum - 2*s0  ==  (sum - s0) + (p - s0)   (kept non-negative)
-    uint64_t s0 = sum - s[0] + (uint64_t)(P - s[0]);
-    uint32_t out0 = monty_reduce(s0);
+    // sigma = sum * 2^-32 mod p, canonical (sum < 2^36)
+    uint32_t slo = (uint32_t)sum, shi = (uint32_t)(sum >> 32);
+    uint32_t r = shi - kb::mulhi(slo * MU, kb::P);
+    const uint32_t sigma = umin(r, r + kb::P);
+    const uint32_t sigma_p = sigma + kb::P;
+    // lane 0: sigma - 2 * x0 * 2^-32 = sigma + 2 * hi(m * p)   (x0 canonical; x0 * 2^-32 = -hi(m p))
+    uint32_t q0 = kb::mulhi(s[0] * MU, kb::P);
+    uint32_t y0 = kb::add(sigma, kb::add(q0, q0));  // (3p does not fit 32 bits: reduce as we go)
+    // lane 1 (k = 0): t_hi = 0
+    s[1] = sigma_p - kb::mulhi(s[1] * MU, kb::P);
 #pragma unroll
-    for (int i = 1; i < 16; i++) {
-        const int sh = (i == 15) ? 15 : (i - 1);
-        s[i] = monty_reduce(sum + ((uint64_t)s[i] << sh));
+    for (int i = 2; i < 16; i++) {
+        const int k = (i == 15) ? 15 : (i - 1);
+        uint32_t tlo = s[i] << k, thi = s[i] >> (32 - k);
+        s[i] = sigma_p + thi - kb::mulhi(tlo * MU, kb::P);
     }
-    s[0] = out0;
+    s[0] = y0;
 }
 
-__device__ __forceinline__ void permute(uint32_t (&s)[16]) {
+KB_HD void permute(uint32_t (&s)[16]) {
     ext_layer(s);
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) s[i] = sbox(s[i], RC.ext[r * 16 + i]);
+        for (int i = 0; i < 16; i++) s[i] = sbox(s[i], P2_RC.ext[r * 16 + i]);
         ext_layer(s);
     }
 #pragma unroll 1
     for (int r = 0; r < 20; r++) {
-        s[0] = sbox(s[0], RC.inr[r]);
-        int_layer(s);
+        s[0] = sbox(s[0], P2_RC.inr[r]);
+        int_layer_lazy(s);
     }
+    // lanes 1..15 back to canonical (< 2p + 2^15 < 3p)
+#pragma unroll
+    for (int i = 1; i < 16; i++) { uint32_t v = s[i]; v = umin(v, v - kb::P); s[i] = umin(v, v - kb::P); }
 #pragma unroll 1
     for (int r = 4; r < 8; r++) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) s[i] = sbox(s[i], RC.ext[r * 16 + i]);
+        for (int i = 0; i < 16; i++) s[i] = sbox(s[i], P2_RC.ext[r * 16 + i]);
         ext_layer(s);
     }
 }
 
 // compress(L, R) = permute(L || R)[0..8]
-__device__ __forceinline__ void compress(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t (&out)[8]) {
+KB_HD void compress(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t (&out)[8]) {
     uint32_t s[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) { s[i] = l[i]; s[8 + i] = r[i]; }

@@ -54,11 +54,12 @@ def load():
 ERR_FUNCS = [
     "sp1b200_ctx_create", "sp1b200_ctx_sync", "sp1b200_malloc", "sp1b200_free", "sp1b200_memcpy_h2d",
     "sp1b200_memcpy_d2h", "sp1b200_poseidon2_permute", "sp1b200_rs_encode", "sp1b200_merkle_commit", "sp1b200_grind",
-    "sp1b200_stacked_commit", "sp1b200_stacked_prove",
+    "sp1b200_stacked_commit", "sp1b200_stacked_prove", "sp1b200_jagged_commit", "sp1b200_jagged_column_claims",
+    "sp1b200_jagged_prove",
 ]
 OTHER_FUNCS = ["sp1b200_challenger_init", "sp1b200_challenger_observe", "sp1b200_challenger_sample",
                "sp1b200_challenger_sample_bits", "sp1b200_challenger_check_witness", "sp1b200_ctx_destroy", "sp1b200_default_core_params", "sp1b200_version", "sp1b200_ctx_stream",
-               "sp1b200_launch_count", "sp1b200_last_phase_ms", "sp1b200_commit_free"]
+               "sp1b200_launch_count", "sp1b200_last_phase_ms", "sp1b200_commit_free", "sp1b200_jagged_round_free"]
 
 
 def _ptr(a):
@@ -158,6 +159,46 @@ class Lib:
         self._chk(self.L.sp1b200_stacked_prove(self.ctx, arr, C.c_uint32(n), _ptr(point), C.c_uint32(point.shape[0]),
                                                _ptr(rw), _ptr(challenger_state), _ptr(proof), C.c_uint64(cap_words),
                                                C.byref(nwords)))
+        return proof[:nwords.value].copy()
+
+    def jagged_commit(self, tables, keep_codeword=True):
+        """tables: list of [cols, rows] uint32 arrays (rows may be 0).  -> (commit[8], handle, shapes)"""
+        rows = [int(t.shape[1]) for t in tables]
+        cols = [int(t.shape[0]) for t in tables]
+        parts = [np.ascontiguousarray(t, dtype=np.uint32).reshape(-1) for t in tables if t.shape[1]]
+        dense = np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(1, np.uint32)
+        return self.jagged_commit_dense(dense, rows, cols, keep_codeword)
+
+    def jagged_commit_dense(self, dense, rows, cols, keep_codeword=True):
+        """dense: flat uint32 (numpy or cuda tensor) of all real cells, tables back to back, column-major each"""
+        n = len(rows)
+        R = (C.c_uint64 * n)(*rows)
+        Cc = (C.c_uint64 * n)(*cols)
+        commit = np.zeros(8, np.uint32)
+        h = C.c_void_p()
+        self._chk(self.L.sp1b200_jagged_commit(self.ctx, _ptr(dense), C.c_uint32(n), R, Cc, C.c_int(int(keep_codeword)),
+                                               _ptr(commit), C.byref(h)))
+        return commit, h
+
+    def jagged_round_free(self, handle):
+        self.L.sp1b200_jagged_round_free(self.ctx, handle)
+
+    def jagged_column_claims(self, handle, z_row, ncols_total):
+        z = np.ascontiguousarray(z_row, dtype=np.uint32)
+        out = np.zeros((ncols_total, 4), np.uint32)
+        self._chk(self.L.sp1b200_jagged_column_claims(self.ctx, handle, _ptr(z), _ptr(out)))
+        return out
+
+    def jagged_prove(self, handles, z_row, claims, challenger_state, replay=None, cap_words=1 << 24):
+        n = len(handles)
+        arr = (C.c_void_p * n)(*[h.value for h in handles])
+        z = np.ascontiguousarray(z_row, dtype=np.uint32)
+        cl = np.ascontiguousarray(claims, dtype=np.uint32)
+        proof = np.zeros(cap_words, np.uint32)
+        nwords = C.c_uint64()
+        rw = None if replay is None else np.ascontiguousarray(replay, dtype=np.uint32)
+        self._chk(self.L.sp1b200_jagged_prove(self.ctx, arr, C.c_uint32(n), _ptr(z), _ptr(cl), _ptr(rw),
+                                              _ptr(challenger_state), _ptr(proof), C.c_uint64(cap_words), C.byref(nwords)))
         return proof[:nwords.value].copy()
 
     def grind(self, state34, bits):

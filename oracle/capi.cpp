@@ -1,9 +1,10 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see field.hpp header).  PARITY UNPINNED BY STORED FIXTURES.
 // C entry points for tests/ (ctypes), __graft_entry__.smoke() and bench.py's cpu_baseline leg.
 // All field elements cross this boundary as u32 Montgomery words (the reference's in-memory form).
-#include "jagged.hpp"
+#include "zerocheck.hpp"
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -70,7 +71,15 @@ static void chal_store(const Challenger& c, uint32_t* s) {
     s[32] = (uint32_t)c.nin; s[33] = (uint32_t)c.nout;
 }
 
+static int g_skip_verify = 0;
+static double g_times[4] = {0, 0, 0, 0};  // seconds: claims, commit (all rounds, last round separately), prove
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 extern "C" {
+
+// bench.py cpu_baseline support: skip the (restated) verifier and report the phase times of the last jagged run
+void orc_set_skip_verify(int v) { g_skip_verify = v; }
+void orc_last_times(double* out4) { for (int i = 0; i < 4; i++) out4[i] = g_times[i]; }
 
 int orc_num_threads() {
 #ifdef _OPENMP
@@ -221,7 +230,10 @@ int64_t orc_jagged_prove_verify(const uint32_t* const* dense, uint32_t n_rounds,
             p += tb.rows * tb.cols;
             tabs.push_back(tb);
         }
+        double tc0 = now_s();
         rounds.push_back(jagged_commit(tabs, log_stack, max_log_rows, fp));
+        g_times[2] = now_s() - tc0;               // commit time of the last (main) round
+        g_times[1] = (r == 0 ? 0.0 : g_times[1]) + g_times[2];
         commits.push_back(rounds.back().commit);
         for (int i = 0; i < 8; i++) commits_out[r * 8 + i] = commits.back().d[i].v;
         for (auto& e : cl) for (int i = 0; i < 4; i++) claims_out[co++] = e.c[i].v;
@@ -231,13 +243,86 @@ int64_t orc_jagged_prove_verify(const uint32_t* const* dense, uint32_t n_rounds,
     Challenger vch = ch;
     F rw[2];
     if (replay_witnesses) { rw[0] = F::raw(replay_witnesses[0]); rw[1] = F::raw(replay_witnesses[1]); }
+    double tp0 = now_s();
     JaggedProof pf = jagged_prove(z_row, claims, rounds, max_log_rows, ch, fp, replay_witnesses ? rw : nullptr);
+    g_times[3] = now_s() - tp0;
     chal_store(ch, challenger_state);
-    const char* err = jagged_verify(commits, z_row, claims, pf, vch, log_stack, max_log_rows, fp);
+    const char* err = g_skip_verify ? nullptr : jagged_verify(commits, z_row, claims, pf, vch, log_stack, max_log_rows, fp);
     if (err) { std::fprintf(stderr, "oracle jagged verifier rejected oracle proof: %s\n", err); return -1; }
     std::vector<uint32_t> o;
     put(o, pf);
     if (proof_out) { if (o.size() > proof_cap) return -2; std::copy(o.begin(), o.end(), proof_out); }
+    return (int64_t)o.size();
+}
+
+
+}  // extern "C"
+
+// ---- machine blob: the AIR bytecode of every chip as u32 words (layout documented in include/sp1b200.h) ------------
+// [n_chips] then per chip: main_w prep_w n_constraints n_regs n_instrs n_leaves n_consts n_publics n_asserts,
+// instrs (2 words each = the 8-byte DagInstr), leaves (2 words each = LeafRef), consts, publics, assert_regs, assert_alphas
+struct MachineChip { AirProgram air; uint32_t main_w, prep_w; };
+static std::vector<MachineChip> parse_machine(const uint32_t* b) {
+    uint32_t n = *b++;
+    std::vector<MachineChip> out(n);
+    for (auto& c : out) {
+        c.main_w = *b++; c.prep_w = *b++; c.air.n_constraints = *b++; c.air.n_regs = *b++;
+        uint32_t ni = *b++, nl = *b++, nc = *b++, np = *b++, na = *b++;
+        for (uint32_t i = 0; i < ni; i++, b += 2) { DagInstr d; std::memcpy(&d, b, 8); c.air.instrs.push_back(d); }
+        for (uint32_t i = 0; i < nl; i++, b += 2) { LeafRef l; std::memcpy(&l, b, 8); c.air.leaves.push_back(l); }
+        for (uint32_t i = 0; i < nc; i++) c.air.consts.push_back(F::raw(*b++));
+        for (uint32_t i = 0; i < np; i++) c.air.publics.push_back(*b++);
+        for (uint32_t i = 0; i < na; i++) c.air.assert_regs.push_back((uint16_t)*b++);
+        for (uint32_t i = 0; i < na; i++) c.air.assert_alphas.push_back(*b++);
+    }
+    return out;
+}
+
+extern "C" {
+
+// ---- zerocheck stand-alone: sample (alpha, gamma) as prove_shard_with_data does, prove, verify with the restated
+// ShardVerifier::verify_zerocheck.  heights[k]; main[k]/prep[k]: column-major [w x height]; gkr_point: max_log_rows ext.
+// openings_out: per chip main evals then prep evals AT gkr_point (what LogUp-GKR would hand over).
+// out words: sumcheck proof | per chip {prep evals, main evals} at the zerocheck point.
+int64_t orc_zerocheck_prove_verify(const uint32_t* machine_blob, const uint64_t* heights, const uint32_t* const* main, const uint32_t* const* prep,
+                                   const uint32_t* pv_words, uint32_t n_pv, uint32_t max_log_rows, const uint32_t* gkr_point_words,
+                                   uint32_t* challenger_state, uint32_t* openings_out, uint32_t* out, uint64_t cap) {
+    std::vector<MachineChip> mc = parse_machine(machine_blob);
+    std::vector<F> pv(n_pv);
+    for (uint32_t i = 0; i < n_pv; i++) pv[i] = F::raw(pv_words[i]);
+    std::vector<EF> gp(max_log_rows);
+    for (uint32_t i = 0; i < max_log_rows; i++) gp[i] = EF::from_base_slice(asF(gkr_point_words + 4 * i));
+    std::vector<EF> eq = partial_lagrange(gp);
+    std::vector<ZcChip> chips(mc.size());
+    std::vector<std::vector<EF>> om(mc.size()), op(mc.size());
+    size_t oo = 0;
+    for (size_t k = 0; k < mc.size(); k++) {
+        ZcChip& c = chips[k];
+        c.air = &mc[k].air; c.height = heights[k]; c.main_w = mc[k].main_w; c.prep_w = mc[k].prep_w;
+        c.main = asF(main[k]); c.prep = c.prep_w ? asF(prep[k]) : nullptr;
+        for (size_t j = 0; j < c.main_w; j++) { EF a; for (size_t r = 0; r < c.height; r++) a += eq[r] * c.main[j * c.height + r]; om[k].push_back(a); }
+        for (size_t j = 0; j < c.prep_w; j++) { EF a; for (size_t r = 0; r < c.height; r++) a += eq[r] * c.prep[j * c.height + r]; op[k].push_back(a); }
+        for (auto& e : om[k]) for (int i = 0; i < 4; i++) openings_out[oo++] = e.c[i].v;
+        for (auto& e : op[k]) for (int i = 0; i < 4; i++) openings_out[oo++] = e.c[i].v;
+    }
+    Challenger ch; chal_load(ch, challenger_state);
+    Challenger vch = ch;
+    EF alpha = ch.sample_ext(), gamma = ch.sample_ext();
+    std::vector<EF> claims(mc.size());
+    for (size_t k = 0; k < mc.size(); k++) {
+        EF g = gamma, a;
+        for (auto& e : om[k]) { a += e * g; g *= gamma; }
+        for (auto& e : op[k]) { a += e * g; g *= gamma; }
+        claims[k] = a;
+    }
+    ZerocheckResult r = zerocheck_prove(chips, alpha, gamma, gp, claims, pv, max_log_rows, ch);
+    chal_store(ch, challenger_state);
+    const char* err = zerocheck_verify(chips, r.opened, gp, om, op, r.proof, pv, max_log_rows, vch);
+    if (err) { std::fprintf(stderr, "oracle zerocheck verifier rejected oracle proof: %s\n", err); return -1; }
+    std::vector<uint32_t> o;
+    put(o, r.proof);
+    for (auto& c : r.opened) { for (auto& e : c.prep) put(o, e); for (auto& e : c.main) put(o, e); }
+    if (out) { if (o.size() > cap) return -2; std::copy(o.begin(), o.end(), out); }
     return (int64_t)o.size();
 }
 

@@ -182,6 +182,10 @@ static inline PartialSumcheckProof jagged_eval_prove(const JaggedParams& jp, con
     EF claim = expected_sum;
     for (size_t round = 0; round < dim; round++) {
         EF y0, yh;
+#pragma omp parallel
+        {
+        EF ly0, lyh;
+#pragma omp for schedule(dynamic, 8) nowait
         for (size_t k = 0; k < merged.size(); k++) {
             for (int which = 0; which < 2; which++) {
                 EF lambda = which ? half : EF();
@@ -194,8 +198,11 @@ static inline PartialSumcheckProof jagged_eval_prove(const JaggedParams& jp, con
                 hp.insert(hp.end(), rhos.begin(), rhos.end());
                 std::vector<EF> left(hp.begin(), hp.begin() + hp.size() / 2), right(hp.begin() + hp.size() / 2, hp.end());
                 EF v = zc[k] * bp.eval(left, right) * eq_eval;
-                if (which) yh += v; else y0 += v;
+                if (which) lyh += v; else ly0 += v;
             }
+        }
+#pragma omp critical
+        { y0 += ly0; yh += lyh; }
         }
         EF y1 = claim - y0;
         Uni poly = interpolate({EF(), half, EF::one()}, {y0, yh, y1});

@@ -1,0 +1,124 @@
+"""Synthetic AIRs in the reference GPU prover's bytecode format, with traces that satisfy them.
+
+The reference lowers each chip's Rust `Air::eval` to `ChunkBytecode` (sp1-gpu/crates/air/src/ir/bytecode.rs, consumed by
+sp1-gpu/crates/sys/lib/zerocheck/sequential.cu:52-110).  That lowering needs cargo, which this image lacks, so tests and
+bench use synthetic chips expressed directly in the same instruction set (DagInstr / LeafRef / BcOp, layout of
+sp1-gpu/crates/sys/include/zerocheck/sequential.cuh:13-49): the prover input contract is unchanged.
+
+Column template (repeated `groups` times in the main trace), constraints of degree <= 3:
+    a, b free;  d in {0,1};  c = a*b;  e = a*b*d;  f = a + K*pv[0]      (+ with preprocessed column g:  h = g*a)
+so all-zero padding rows violate the `f` constraint by a constant — exercising the padded-row correction.
+Test/bench input generation only.
+"""
+import numpy as np
+
+P = 0x7F000001
+LOAD_LEAF, LOAD_CONST, LOAD_PUBLIC, ADD, SUB, MUL, NEG = range(7)
+LEAF_PREP, LEAF_MAIN = 2, 4
+
+
+def to_monty(x):
+    x = np.asarray(x, dtype=np.uint64)
+    return ((x << np.uint64(32)) % np.uint64(P)).astype(np.uint32)
+
+
+class Asm:
+    def __init__(self):
+        self.instrs, self.leaves, self.consts, self.publics, self.asserts = [], [], [], [], []
+        self.nreg = 0
+
+    def _r(self):
+        self.nreg += 1
+        return self.nreg - 1
+
+    def leaf(self, source, col):
+        self.leaves.append((source, col))
+        r = self._r()
+        self.instrs.append((LOAD_LEAF, r, len(self.leaves) - 1, 0))
+        return r
+
+    def const(self, canonical):
+        self.consts.append(int(to_monty(np.array([canonical]))[0]))
+        r = self._r()
+        self.instrs.append((LOAD_CONST, r, len(self.consts) - 1, 0))
+        return r
+
+    def public(self, idx):
+        self.publics.append(idx)
+        r = self._r()
+        self.instrs.append((LOAD_PUBLIC, r, len(self.publics) - 1, 0))
+        return r
+
+    def op(self, opc, a, b=0):
+        r = self._r()
+        self.instrs.append((opc, r, a, b))
+        return r
+
+    def assert_zero(self, reg):
+        self.asserts.append(reg)
+
+    def words(self, main_w, prep_w):
+        n = len(self.asserts)
+        w = [main_w, prep_w, n, self.nreg, len(self.instrs), len(self.leaves), len(self.consts), len(self.publics), n]
+        for opc, out, a, b in self.instrs:
+            w += [opc | (out << 16), a | (b << 16)]
+        for src, col in self.leaves:
+            w += [src, col]
+        w += self.consts + self.publics + self.asserts + list(range(n))  # constraint i <-> reversed-powers index i
+        return w
+
+
+def synth_chip(groups, with_prep, kconst=7):
+    """-> (machine words for this chip, main_w, prep_w)"""
+    a = Asm()
+    main_w = 6 * groups + (1 if with_prep else 0)
+    prep_w = 1 if with_prep else 0
+    pv0 = a.public(0)
+    kc = a.const(kconst)
+    one = a.const(1)
+    kpv = a.op(MUL, kc, pv0)
+    for g in range(groups):
+        A, B, Cc, D, E, Fc = (a.leaf(LEAF_MAIN, 6 * g + i) for i in range(6))
+        ab = a.op(MUL, A, B)
+        a.assert_zero(a.op(SUB, Cc, ab))                       # c - a b
+        a.assert_zero(a.op(MUL, D, a.op(SUB, D, one)))         # d (d - 1)
+        a.assert_zero(a.op(SUB, E, a.op(MUL, ab, D)))          # e - a b d   (degree 3)
+        a.assert_zero(a.op(SUB, Fc, a.op(ADD, A, kpv)))        # f - (a + K pv0)
+    if with_prep:
+        G = a.leaf(LEAF_PREP, 0)
+        H = a.leaf(LEAF_MAIN, 6 * groups)
+        A0 = a.leaf(LEAF_MAIN, 0)
+        a.assert_zero(a.op(ADD, a.op(NEG, a.op(MUL, G, A0)), H))  # -(g a) + h
+    return a.words(main_w, prep_w), main_w, prep_w
+
+
+def synth_trace(rng, height, groups, with_prep, pv0_canonical, kconst=7):
+    """canonical-domain generation, returned as Montgomery words, column-major [w, height]"""
+    cols = []
+    prep = None
+    a0 = None
+    for g in range(groups):
+        a = rng.integers(0, P, height, dtype=np.uint64)
+        b = rng.integers(0, P, height, dtype=np.uint64)
+        d = rng.integers(0, 2, height, dtype=np.uint64)
+        c = a * b % P
+        e = c * d % P
+        f = (a + kconst * pv0_canonical) % P
+        cols += [a, b, c, d, e, f]
+        if g == 0:
+            a0 = a
+    if with_prep:
+        gcol = rng.integers(0, P, height, dtype=np.uint64)
+        cols.append(gcol * a0 % P)
+        prep = to_monty(np.stack([gcol]))
+    main = to_monty(np.stack(cols)) if height else np.zeros((len(cols), 0), np.uint32)
+    if with_prep and not height:
+        prep = np.zeros((1, 0), np.uint32)
+    return main, prep
+
+
+def machine_blob(chip_words):
+    w = [len(chip_words)]
+    for cw in chip_words:
+        w += cw
+    return np.array(w, dtype=np.uint32)

@@ -210,3 +210,32 @@ def jagged_prove_verify(rounds_tables, log_stack, max_log_rows, z_row, challenge
 def random_tables(rng, shapes):
     """shapes: list of (rows, cols) -> list of [cols, rows] Montgomery arrays"""
     return [rand_field(rng, (c, r)) if r else np.zeros((c, 0), np.uint32) for r, c in shapes]
+
+
+def zerocheck_prove_verify(blob, heights, mains, preps, pv, max_log_rows, gkr_point, challenger):
+    """mains/preps: per chip [w, height] arrays (preps[k] None when the chip has no preprocessed columns).
+    Returns (gkr openings per chip flat [sum(main_w+prep_w), 4], proof+opened words)."""
+    n = len(heights)
+    keep = []
+
+    def arr_ptr(a):
+        a = np.ascontiguousarray(a if a is not None and a.size else np.zeros(1, np.uint32), dtype=np.uint32)
+        keep.append(a)
+        return ptr(a)
+    M = (u32p * n)(*[arr_ptr(m) for m in mains])
+    Pp = (u32p * n)(*[arr_ptr(p) for p in preps])
+    H = (C.c_uint64 * n)(*heights)
+    blob = np.ascontiguousarray(blob, dtype=np.uint32)
+    pv = np.ascontiguousarray(pv, dtype=np.uint32)
+    gp = np.ascontiguousarray(gkr_point, dtype=np.uint32)
+    ncols = sum(m.shape[0] for m in mains) + sum(p.shape[0] for p in preps if p is not None)
+    openings = np.zeros((ncols, 4), np.uint32)
+    cap = 1 << 22
+    out = np.zeros(cap, np.uint32)
+    f = lib().orc_zerocheck_prove_verify
+    f.restype = C.c_int64
+    nw = f(ptr(blob), H, M, Pp, ptr(pv), C.c_uint32(pv.size), C.c_uint32(max_log_rows), ptr(gp), ptr(challenger.st),
+           ptr(openings), ptr(out), C.c_uint64(cap))
+    if nw < 0:
+        raise RuntimeError(f"oracle zerocheck failed ({nw})")
+    return openings, out[:nw].copy()

@@ -156,6 +156,36 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
                                  uint32_t* h_challenger34, uint32_t* h_proof, uint64_t proof_cap_words,
                                  uint64_t* h_proof_words);
 
+/* ---- zerocheck (replaces sp1-gpu/crates/zerocheck + sys/lib/zerocheck/*.cu) ------------------------------------ */
+
+typedef struct sp1b200_machine sp1b200_machine; /* the machine's AIR constraints, uploaded once */
+
+/* Upload the constraint bytecode of every chip (replaces upload_machine_bytecode, sp1-gpu/crates/zerocheck/src/prover.rs).
+ * The instruction set and record layouts are the reference GPU prover's (sys/include/zerocheck/sequential.cuh:13-49):
+ *   DagInstr {u8 opcode, u8 pad, u16 out, u16 a, u16 b}, LeafRef {u8 source(2 = preprocessed, 4 = main), u8 pad, u16 pad, u32 col},
+ *   opcodes LOAD_LEAF 0, LOAD_CONST 1, LOAD_PUBLIC 2, ADD 3, SUB 4, MUL 5, NEG 6; asserts = (register, alpha index) pairs
+ *   with alpha index i <-> alpha^(n_constraints-1-i) (Horner order of the verifier folder).
+ * Blob words: [n_chips] then per chip (chips in BTreeSet/name order):
+ *   main_w prep_w n_constraints n_regs n_instrs n_leaves n_consts n_publics n_asserts,
+ *   instrs (2 words each), leaves (2 words each), consts (Montgomery), publics (indices), assert_regs, assert_alphas. */
+sp1b200_err sp1b200_machine_create(sp1b200_ctx* ctx, const uint32_t* h_blob, uint64_t n_words, sp1b200_machine** out);
+void sp1b200_machine_free(sp1b200_ctx* ctx, sp1b200_machine* machine);
+uint32_t sp1b200_machine_num_chips(const sp1b200_machine* machine);
+
+/* ShardProver::zerocheck (crates/hypercube/src/prover/shard.rs:474-646): samples lambda, runs the max_log_row_count-round
+ * sumcheck over all chips (round polynomial through nodes {0,1,2,4,b}, crates/hypercube/src/prover/zerocheck/sum_as_poly.rs:187-287),
+ * observes and returns the opened values.  d_main[k]/d_prep[k]: device pointers to chip k's columns, column-major
+ * [w x h_heights[k]] (d_prep[k] may be NULL when the chip has no preprocessed columns); h_alpha/h_gamma: the two ext
+ * challenges the caller sampled after LogUp-GKR (shard.rs:707-709); h_claims: per chip sum_j gamma^(j+1) * opening_j
+ * (main columns then preprocessed) of the LogUp-GKR openings at h_gkr_point.
+ * Output words: sumcheck proof {n_polys, per poly {n_coeffs, coeffs ext}, claimed_sum, point, eval} |
+ *               per chip {preprocessed evaluations ext[prep_w], main evaluations ext[main_w]} at the sumcheck point. */
+sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* machine, const uint64_t* h_heights,
+                              const uint32_t* const* d_main, const uint32_t* const* d_prep, const uint32_t* h_public_values,
+                              uint32_t n_public_values, const uint32_t* h_gkr_point, const uint32_t* h_alpha,
+                              const uint32_t* h_gamma, const uint32_t* h_claims, uint32_t* h_challenger34, uint32_t* h_out,
+                              uint64_t out_cap_words, uint64_t* h_out_words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,7 @@ def load():
         L.sp1b200_last_phase_ms.restype = C.c_float
         L.sp1b200_challenger_sample_bits.restype = C.c_uint32
         L.sp1b200_challenger_check_witness.restype = C.c_int
+        L.sp1b200_machine_num_chips.restype = C.c_uint32
         for name in ERR_FUNCS:
             getattr(L, name).restype = C.c_char_p
         _cdll = L
@@ -55,11 +56,12 @@ ERR_FUNCS = [
     "sp1b200_ctx_create", "sp1b200_ctx_sync", "sp1b200_malloc", "sp1b200_free", "sp1b200_memcpy_h2d",
     "sp1b200_memcpy_d2h", "sp1b200_poseidon2_permute", "sp1b200_rs_encode", "sp1b200_merkle_commit", "sp1b200_grind",
     "sp1b200_stacked_commit", "sp1b200_stacked_prove", "sp1b200_jagged_commit", "sp1b200_jagged_column_claims",
-    "sp1b200_jagged_prove",
+    "sp1b200_jagged_prove", "sp1b200_machine_create", "sp1b200_zerocheck",
 ]
 OTHER_FUNCS = ["sp1b200_challenger_init", "sp1b200_challenger_observe", "sp1b200_challenger_sample",
                "sp1b200_challenger_sample_bits", "sp1b200_challenger_check_witness", "sp1b200_ctx_destroy", "sp1b200_default_core_params", "sp1b200_version", "sp1b200_ctx_stream",
-               "sp1b200_launch_count", "sp1b200_last_phase_ms", "sp1b200_commit_free", "sp1b200_jagged_round_free"]
+               "sp1b200_launch_count", "sp1b200_last_phase_ms", "sp1b200_commit_free", "sp1b200_jagged_round_free",
+               "sp1b200_machine_free", "sp1b200_machine_num_chips"]
 
 
 def _ptr(a):
@@ -200,6 +202,33 @@ class Lib:
         self._chk(self.L.sp1b200_jagged_prove(self.ctx, arr, C.c_uint32(n), _ptr(z), _ptr(cl), _ptr(rw),
                                               _ptr(challenger_state), _ptr(proof), C.c_uint64(cap_words), C.byref(nwords)))
         return proof[:nwords.value].copy()
+
+    # -- zerocheck --------------------------------------------------------------------------------------------
+    def machine_create(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint32)
+        h = C.c_void_p()
+        self._chk(self.L.sp1b200_machine_create(self.ctx, _ptr(blob), C.c_uint64(blob.size), C.byref(h)))
+        return h
+
+    def machine_free(self, h):
+        self.L.sp1b200_machine_free(self.ctx, h)
+
+    def zerocheck(self, machine, heights, d_mains, d_preps, pv, gkr_point, alpha, gamma, claims, challenger_state, cap_words=1 << 22):
+        """d_mains / d_preps: per chip device tensors (or None).  Returns output words (proof | opened values)."""
+        n = len(heights)
+        H = (C.c_uint64 * n)(*heights)
+        M = (C.c_void_p * n)(*[t.data_ptr() if t is not None and t.numel() else None for t in d_mains])
+        Pp = (C.c_void_p * n)(*[t.data_ptr() if t is not None and t.numel() else None for t in d_preps])
+        pv = np.ascontiguousarray(pv, dtype=np.uint32)
+        out = np.zeros(cap_words, np.uint32)
+        nw = C.c_uint64()
+        self._chk(self.L.sp1b200_zerocheck(self.ctx, machine, H, M, Pp, _ptr(pv), C.c_uint32(pv.size),
+                                           _ptr(np.ascontiguousarray(gkr_point, dtype=np.uint32)),
+                                           _ptr(np.ascontiguousarray(alpha, dtype=np.uint32)),
+                                           _ptr(np.ascontiguousarray(gamma, dtype=np.uint32)),
+                                           _ptr(np.ascontiguousarray(claims, dtype=np.uint32)), _ptr(challenger_state), _ptr(out),
+                                           C.c_uint64(cap_words), C.byref(nw)))
+        return out[:nw.value].copy()
 
     def grind(self, state34, bits):
         st = np.ascontiguousarray(state34, dtype=np.uint32).copy()

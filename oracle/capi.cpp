@@ -1,7 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see field.hpp header).  PARITY UNPINNED BY STORED FIXTURES.
 // C entry points for tests/ (ctypes), __graft_entry__.smoke() and bench.py's cpu_baseline leg.
 // All field elements cross this boundary as u32 Montgomery words (the reference's in-memory form).
-#include "zerocheck.hpp"
+#include "gkr.hpp"
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
@@ -262,7 +262,7 @@ int64_t orc_jagged_prove_verify(const uint32_t* const* dense, uint32_t n_rounds,
 // [n_chips] then per chip: main_w prep_w n_constraints n_regs n_instrs n_leaves n_consts n_publics n_asserts,
 // instrs (2 words each = the 8-byte DagInstr), leaves (2 words each = LeafRef), consts, publics, assert_regs, assert_alphas
 struct MachineChip { AirProgram air; uint32_t main_w, prep_w; };
-static std::vector<MachineChip> parse_machine(const uint32_t* b) {
+static std::vector<MachineChip> parse_machine(const uint32_t* b, const uint32_t** end_out = nullptr) {
     uint32_t n = *b++;
     std::vector<MachineChip> out(n);
     for (auto& c : out) {
@@ -274,6 +274,28 @@ static std::vector<MachineChip> parse_machine(const uint32_t* b) {
         for (uint32_t i = 0; i < np; i++) c.air.publics.push_back(*b++);
         for (uint32_t i = 0; i < na; i++) c.air.assert_regs.push_back((uint16_t)*b++);
         for (uint32_t i = 0; i < na; i++) c.air.assert_alphas.push_back(*b++);
+    }
+    if (end_out) *end_out = b;
+    return out;
+}
+
+// interactions section (follows the AIR records): per chip [n_interactions] then per interaction
+//   is_send arg_index n_values, multiplicity vcol, value vcols;  vcol = n_terms constant(Montgomery) {source col weight(Montgomery)}*
+static const uint32_t* parse_vcol(const uint32_t* b, VCol& v) {
+    uint32_t nt = *b++; v.constant = F::raw(*b++);
+    for (uint32_t i = 0; i < nt; i++) { VTerm t; t.source = (uint8_t)b[0]; t.col = b[1]; t.weight = F::raw(b[2]); b += 3; v.terms.push_back(t); }
+    return b;
+}
+static std::vector<std::vector<Interaction>> parse_interactions(const uint32_t* b, size_t n_chips) {
+    std::vector<std::vector<Interaction>> out(n_chips);
+    for (auto& chip : out) {
+        uint32_t n = *b++;
+        for (uint32_t i = 0; i < n; i++) {
+            Interaction in; in.is_send = *b++ != 0; in.arg_index = *b++; uint32_t nv = *b++;
+            b = parse_vcol(b, in.mult);
+            for (uint32_t k = 0; k < nv; k++) { VCol v; b = parse_vcol(b, v); in.values.push_back(v); }
+            chip.push_back(in);
+        }
     }
     return out;
 }
@@ -322,6 +344,44 @@ int64_t orc_zerocheck_prove_verify(const uint32_t* machine_blob, const uint64_t*
     std::vector<uint32_t> o;
     put(o, r.proof);
     for (auto& c : r.opened) { for (auto& e : c.prep) put(o, e); for (auto& e : c.main) put(o, e); }
+    if (out) { if (o.size() > cap) return -2; std::copy(o.begin(), o.end(), out); }
+    return (int64_t)o.size();
+}
+
+
+static void put(std::vector<uint32_t>& o, const GkrProof& p) {
+    o.push_back((uint32_t)p.out_num.size());
+    for (auto& e : p.out_num) put(o, e);
+    for (auto& e : p.out_den) put(o, e);
+    o.push_back((uint32_t)p.rounds.size());
+    for (auto& r : p.rounds) { put(o, r.n0); put(o, r.n1); put(o, r.d0); put(o, r.d1); put(o, r.sc); }
+    for (auto& e : p.point) put(o, e);
+    for (size_t k = 0; k < p.main_open.size(); k++) { for (auto& e : p.main_open[k]) put(o, e); for (auto& e : p.prep_open[k]) put(o, e); }
+    put(o, p.witness);
+}
+
+// ---- LogUp-GKR stand-alone: prove + restated verify_logup_gkr.  Words out: n_out | numerator[n_out] | denominator[n_out] |
+// n_rounds | per round {numerator_0 numerator_1 denominator_0 denominator_1 sumcheck} | point | per chip {main openings, prep openings} | witness
+int64_t orc_gkr_prove_verify(const uint32_t* machine_blob, const uint64_t* heights, const uint32_t* const* main, const uint32_t* const* prep,
+                             uint32_t max_log_rows, uint32_t gkr_pow_bits, const uint32_t* replay_witness, uint32_t* challenger_state,
+                             uint32_t* out, uint64_t cap) {
+    const uint32_t* rest;
+    std::vector<MachineChip> mc = parse_machine(machine_blob, &rest);
+    auto inter = parse_interactions(rest, mc.size());
+    std::vector<GkrChip> chips(mc.size());
+    for (size_t k = 0; k < mc.size(); k++) {
+        chips[k].height = heights[k]; chips[k].main_w = mc[k].main_w; chips[k].prep_w = mc[k].prep_w;
+        chips[k].main = asF(main[k]); chips[k].prep = mc[k].prep_w ? asF(prep[k]) : nullptr; chips[k].inter = inter[k];
+    }
+    Challenger ch; chal_load(ch, challenger_state);
+    Challenger vch = ch;
+    F rw; if (replay_witness) rw = F::raw(*replay_witness);
+    GkrProof pf = gkr_prove(chips, max_log_rows, gkr_pow_bits, ch, replay_witness ? &rw : nullptr);
+    chal_store(ch, challenger_state);
+    const char* err = g_skip_verify ? nullptr : gkr_verify(chips, max_log_rows, gkr_pow_bits, pf, vch);
+    if (err) { std::fprintf(stderr, "oracle gkr verifier rejected oracle proof: %s\n", err); return -1; }
+    std::vector<uint32_t> o;
+    put(o, pf);
     if (out) { if (o.size() > cap) return -2; std::copy(o.begin(), o.end(), out); }
     return (int64_t)o.size();
 }

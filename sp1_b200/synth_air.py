@@ -122,3 +122,52 @@ def machine_blob(chip_words):
     for cw in chip_words:
         w += cw
     return np.array(w, dtype=np.uint32)
+
+
+# ---- LogUp interactions (crates/hypercube/src/lookup/interaction.rs:11-22; VirtualPairCol = Σ weight·column + constant) ----
+def _vcol(terms, constant=0):
+    """terms: [(source, col, weight_canonical)] -> words: n_terms constant {source col weight}*"""
+    w = [len(terms), int(to_monty(np.array([constant]))[0])]
+    for src, col, wt in terms:
+        w += [src, col, int(to_monty(np.array([wt]))[0])]
+    return w
+
+
+def synth_interactions(groups, with_prep):
+    """Balanced sends/receives for a synth_chip: every tuple that is sent is received with the same multiplicity, so the
+    cumulative LogUp sum is zero.  Words for one chip: n_interactions then per interaction
+    is_send arg_index n_values, multiplicity vcol, value vcols."""
+    inter = []
+    for g in range(groups):
+        base = 6 * g
+        a, b, c, d, e, f = (base + i for i in range(6))
+        vals3 = [_vcol([(LEAF_MAIN, a, 1)]), _vcol([(LEAF_MAIN, b, 1), (LEAF_MAIN, a, 2)]), _vcol([(LEAF_MAIN, c, 1)], constant=5)]
+        mult_d = _vcol([(LEAF_MAIN, d, 1)])
+        inter.append((1, 5, mult_d, vals3))                     # send, kind Byte(5), multiplicity d
+        vals1 = [_vcol([(LEAF_MAIN, e, 3)])]
+        inter.append((1, 7, _vcol([], constant=1), vals1))      # send, kind State(7), multiplicity 1
+    for g in range(groups):
+        base = 6 * g
+        a, b, c, d, e, f = (base + i for i in range(6))
+        vals3 = [_vcol([(LEAF_MAIN, a, 1)]), _vcol([(LEAF_MAIN, a, 2), (LEAF_MAIN, b, 1)]), _vcol([(LEAF_MAIN, c, 1)], constant=5)]
+        inter.append((0, 5, _vcol([(LEAF_MAIN, d, 1)]), vals3))  # receive the same tuples
+        inter.append((0, 7, _vcol([], constant=1), [_vcol([(LEAF_MAIN, e, 3)])]))
+    if with_prep:
+        gv = [_vcol([(LEAF_PREP, 0, 1)]), _vcol([(LEAF_MAIN, 6 * groups, 1)])]
+        inter.insert(2 * groups, (1, 2, _vcol([(LEAF_MAIN, 3, 1)]), gv))   # send (g, h) with multiplicity d0
+        inter.append((0, 2, _vcol([(LEAF_MAIN, 3, 1)]), gv))
+    w = [len(inter)]
+    for is_send, kind, mult, vals in inter:
+        w += [is_send, kind, len(vals)] + mult
+        for v in vals:
+            w += v
+    return w
+
+
+def machine_blob_with_interactions(chip_words, inter_words):
+    w = [len(chip_words)]
+    for cw in chip_words:
+        w += cw
+    for iw in inter_words:
+        w += iw
+    return np.array(w, dtype=np.uint32)

@@ -239,3 +239,27 @@ def zerocheck_prove_verify(blob, heights, mains, preps, pv, max_log_rows, gkr_po
     if nw < 0:
         raise RuntimeError(f"oracle zerocheck failed ({nw})")
     return openings, out[:nw].copy()
+
+
+def gkr_prove_verify(blob, heights, mains, preps, max_log_rows, challenger, gkr_pow_bits=12, replay=None):
+    n = len(heights)
+    keep = []
+
+    def arr_ptr(a):
+        a = np.ascontiguousarray(a if a is not None and a.size else np.zeros(1, np.uint32), dtype=np.uint32)
+        keep.append(a)
+        return ptr(a)
+    M = (u32p * n)(*[arr_ptr(m) for m in mains])
+    Pp = (u32p * n)(*[arr_ptr(p) for p in preps])
+    H = (C.c_uint64 * n)(*heights)
+    blob = np.ascontiguousarray(blob, dtype=np.uint32)
+    cap = 1 << 22
+    out = np.zeros(cap, np.uint32)
+    rw = None if replay is None else np.ascontiguousarray([replay], dtype=np.uint32)
+    f = lib().orc_gkr_prove_verify
+    f.restype = C.c_int64
+    nw = f(ptr(blob), H, M, Pp, C.c_uint32(max_log_rows), C.c_uint32(gkr_pow_bits), ptr(rw) if rw is not None else None,
+           ptr(challenger.st), ptr(out), C.c_uint64(cap))
+    if nw < 0:
+        raise RuntimeError(f"oracle gkr failed ({nw})")
+    return out[:nw].copy()

@@ -277,3 +277,33 @@ def test_zerocheck_rejects_violated_constraint():
     ch = O.Challenger()
     with pytest.raises(RuntimeError):
         O.zerocheck_prove_verify(blob, heights, mains, preps, pv, 3, gp, ch)
+
+
+def _synth_machine_gkr(rng, spec, pv0=12345):
+    from sp1_b200 import synth_air as SA
+    words, iwords, mains, preps, heights = [], [], [], [], []
+    for h, g, wp in spec:
+        w, _, _ = SA.synth_chip(g, wp)
+        words.append(w); iwords.append(SA.synth_interactions(g, wp))
+        m, p = SA.synth_trace(rng, h, g, wp, pv0)
+        mains.append(m); preps.append(p); heights.append(h)
+    pv = O.to_monty(np.array([pv0, 5, 6, 7]))
+    return SA.machine_blob_with_interactions(words, iwords), heights, mains, preps, pv
+
+
+@pytest.mark.parametrize("spec,mlr", [
+    ([(8, 1, False)], 3),
+    ([(5, 1, False), (0, 2, False), (6, 1, True)], 3),
+    ([(1, 1, False), (2, 1, True)], 4),
+    ([(32, 2, True), (96, 1, False), (128, 1, False)], 7),
+])
+def test_logup_gkr_roundtrip(spec, mlr):
+    """LogUp-GKR over synthetic balanced interactions -> restated verify_logup_gkr accepts (cumulative sum 0)"""
+    rng = np.random.default_rng(51)
+    blob, heights, mains, preps, pv = _synth_machine_gkr(rng, spec)
+    ch = O.Challenger(); ch.observe(O.rand_field(rng, 4))
+    c1 = ch.clone()
+    words = O.gkr_prove_verify(blob, heights, mains, preps, mlr, c1, gkr_pow_bits=4)
+    c2 = ch.clone()
+    words2 = O.gkr_prove_verify(blob, heights, mains, preps, mlr, c2, gkr_pow_bits=4)
+    assert words.size > 50 and (words == words2).all() and (c1.st == c2.st).all()

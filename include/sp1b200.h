@@ -186,6 +186,24 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* machine, 
                               const uint32_t* h_gamma, const uint32_t* h_claims, uint32_t* h_challenger34, uint32_t* h_out,
                               uint64_t out_cap_words, uint64_t* h_out_words);
 
+/* ---- LogUp-GKR (replaces sp1-gpu/crates/logup_gkr + sys/lib/logup_gkr/*.cu) ---------------------------------------- */
+
+/* The machine blob of sp1b200_machine_create may carry an interactions section after the AIR records
+ * (crates/hypercube/src/lookup/interaction.rs:11-22; VirtualPairCol = sum weight * column + constant):
+ *   per chip: [n_interactions] then per interaction (sends first, then receives):
+ *     is_send arg_index(InteractionKind) n_values, multiplicity vcol, n_values value vcols
+ *   vcol: n_terms constant(Montgomery) { source(2 = preprocessed, 4 = main) col weight(Montgomery) } x n_terms */
+
+/* GkrProverImpl::prove_logup_gkr (crates/hypercube/src/logup_gkr/prover.rs:70-215): grind(gkr_pow_bits), sample alpha / beta seed,
+ * build the fraction-sum circuit over the row variables, observe the circuit output, prove max_log_row_count-1 layers
+ * (logup_poly.rs:230-552), open every chip column at the final trace point.
+ * Output words: n_out | numerator ext[n_out] | denominator ext[n_out] | n_rounds | per round {numerator_0 numerator_1
+ *   denominator_0 denominator_1 ext, sumcheck {n_polys, per poly {n_coeffs, coeffs}, claimed_sum, point, eval}} |
+ *   evaluation point ext[max_log_row_count] | per chip {main openings ext[main_w], preprocessed openings ext[prep_w]} | witness */
+sp1b200_err sp1b200_logup_gkr(sp1b200_ctx* ctx, const sp1b200_machine* machine, const uint64_t* h_heights,
+                              const uint32_t* const* d_main, const uint32_t* const* d_prep, const uint32_t* h_replay_witness,
+                              uint32_t* h_challenger34, uint32_t* h_out, uint64_t out_cap_words, uint64_t* h_out_words);
+
 #ifdef __cplusplus
 }
 #endif

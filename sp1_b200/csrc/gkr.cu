@@ -1,0 +1,322 @@
+// LogUp-GKR on the device.
+// Reference behaviour: crates/hypercube/src/logup_gkr/{prover.rs:70-215, execution.rs:13-382, logup_poly.rs:71-552, cpu.rs:76-226};
+// GPU twin it replaces: sp1-gpu/crates/logup_gkr + sys/lib/logup_gkr/{first_layer,execution,round,lookahead}.cu.
+// HOW (results identical):
+//  * the circuit is kept as ONE fraction sequence per (chip, interaction) and level, F_l[j] (numerator EF, denominator EF),
+//    F_{l+1}[j] = F_l[2j] (+) F_l[2j+1]; the reference's four arrays of a layer are the parity classes of F_l
+//    (numerator_0 = even entries, numerator_1 = odd entries), so no transposition or re-layout is needed between levels;
+//  * every sumcheck round of a layer is one launch over ALL chips (work items are looked up in a small prefix table),
+//    fused as "fix the previous variable + accumulate the next round's three sums";
+//  * once a layer's row variables are exhausted the remaining (interaction) variables range over <= 2^v <= a few
+//    thousand values, which the host transcript driver folds directly.
+#include "ctx.cuh"
+#include "challenger.cuh"
+#include "hostfield.hpp"
+#include "kb31.cuh"
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+#include "machine.cuh"
+
+namespace {
+
+using kb::Ext;
+using hf::E4;
+
+struct TermDev { uint32_t source, col, weight; };
+struct VColDev { uint32_t term_start, n_terms, constant; };
+struct InterDev { uint32_t is_send, arg_index, n_values, vcol_start; };
+
+struct HostInteractions {  // parsed from the machine blob's interaction section
+    std::vector<std::vector<InterDev>> per_chip;
+    std::vector<VColDev> vcols;
+    std::vector<TermDev> terms;
+};
+
+struct ChipJob {           // one chip inside a batched launch
+    uint64_t work_start;   // prefix of work items
+    uint64_t in_off, out_off;  // element offsets of the chip's arrays in the in / out arenas
+    uint32_t rows_in;      // rows (or sequence length) of the input arrays
+    uint32_t I;            // interactions of the chip
+    uint32_t int_off;      // offset into eq_interaction
+    uint32_t pad;
+};
+constexpr int MAX_JOBS = 96;  // 96 * 40 B + 16 B < 4 KB of kernel parameters
+struct JobTable { ChipJob j[MAX_JOBS]; uint32_t n; uint64_t total; };
+
+__device__ __forceinline__ int find_job(const JobTable& t, uint64_t w) {
+    int lo = 0, hi = (int)t.n;  // j[lo].work_start <= w < j[hi].work_start (hi = n: total)
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (t.j[mid].work_start <= w) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__device__ __forceinline__ Ext ldE(const uint32_t* p, uint64_t i) { return kb::ext_load(p + 4 * i); }
+__device__ __forceinline__ void stE(uint32_t* p, uint64_t i, const Ext& e) { kb::ext_store(p + 4 * i, e); }
+
+// ---- level 0: per (chip, interaction k, row r) fraction from the trace (execution.rs:13-36, 114-252) -----------------------
+__global__ void __launch_bounds__(256) gkr_first_level_kernel(const uint32_t* __restrict__ main, const uint32_t* __restrict__ prep, uint64_t h,
+                                                              const InterDev* __restrict__ inter, uint32_t I, const VColDev* __restrict__ vcols,
+                                                              const TermDev* __restrict__ terms, Ext alpha, const uint32_t* __restrict__ betas,
+                                                              uint32_t* __restrict__ num, uint32_t* __restrict__ den) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= h * I) return;
+    const uint32_t k = (uint32_t)(t / h);
+    const uint64_t r = t - (uint64_t)k * h;
+    const InterDev in = inter[k];
+    auto apply = [&](const VColDev& v) {
+        uint32_t acc = v.constant;
+        for (uint32_t q = 0; q < v.n_terms; q++) {
+            const TermDev tm = terms[v.term_start + q];
+            const uint32_t x = __ldg((tm.source == 4 ? main : prep) + (uint64_t)tm.col * h + r);
+            acc = kb::add(acc, kb::mul(x, tm.weight));
+        }
+        return acc;
+    };
+    Ext d = kb::ext_add(alpha, kb::ext_mul_base(ldE(betas, 0), kb::from_canonical(in.arg_index)));
+    for (uint32_t j = 0; j < in.n_values; j++) d = kb::ext_add(d, kb::ext_mul_base(ldE(betas, j + 1), apply(vcols[in.vcol_start + 1 + j])));
+    uint32_t m = apply(vcols[in.vcol_start]);
+    if (!in.is_send) m = kb::neg(m);
+    stE(num, (uint64_t)k * h + r, kb::ext_from_base(m));
+    stE(den, (uint64_t)k * h + r, d);
+}
+
+// ---- level l -> l+1: F'[j] = F[2j] (+) F[2j+1]  (missing odd entry = padding (0,1): identity) ------------------------------
+__global__ void __launch_bounds__(256) gkr_level_kernel(JobTable jobs, const uint32_t* __restrict__ num, const uint32_t* __restrict__ den,
+                                                        uint32_t* __restrict__ num_o, uint32_t* __restrict__ den_o) {
+    uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= jobs.total) return;
+    const ChipJob& c = jobs.j[find_job(jobs, w)];
+    const uint64_t lw = w - c.work_start;
+    const uint32_t len_o = (c.rows_in + 1) / 2;
+    const uint32_t k = (uint32_t)(lw / len_o);
+    const uint32_t j = (uint32_t)(lw - (uint64_t)k * len_o);
+    const uint64_t base = c.in_off + (uint64_t)k * c.rows_in;
+    Ext n0 = ldE(num, base + 2 * j), d0 = ldE(den, base + 2 * j);
+    Ext n = n0, d = d0;
+    if (2 * j + 1 < c.rows_in) {
+        Ext n1 = ldE(num, base + 2 * j + 1), d1 = ldE(den, base + 2 * j + 1);
+        n = kb::ext_add(kb::ext_mul(d1, n0), kb::ext_mul(d0, n1));
+        d = kb::ext_mul(d0, d1);
+    }
+    stE(num_o, c.out_off + (uint64_t)k * len_o + j, n);
+    stE(den_o, c.out_off + (uint64_t)k * len_o + j, d);
+}
+
+// the four layer arrays seen through a fraction sequence F (length len): row i -> (n0,d0) = F[2i], (n1,d1) = F[2i+1]
+struct Row4 { Ext n0, d0, n1, d1; };
+__device__ __forceinline__ Row4 row_from_seq(const uint32_t* num, const uint32_t* den, uint64_t base, uint32_t len, uint32_t i) {
+    Row4 r;
+    r.n0 = kb::ext_zero(); r.n1 = kb::ext_zero(); r.d0 = kb::ext_one(); r.d1 = kb::ext_one();
+    if (2 * i < len) { r.n0 = ldE(num, base + 2 * i); r.d0 = ldE(den, base + 2 * i); }
+    if (2 * i + 1 < len) { r.n1 = ldE(num, base + 2 * i + 1); r.d1 = ldE(den, base + 2 * i + 1); }
+    return r;
+}
+// working layout of a chip (after the first fix): [4][I][rows] EF = n0 | d0 | n1 | d1
+__device__ __forceinline__ Row4 row_from_work(const uint32_t* a, uint64_t base, uint32_t I, uint32_t rows, uint32_t k, uint32_t i) {
+    Row4 r;
+    r.n0 = kb::ext_zero(); r.n1 = kb::ext_zero(); r.d0 = kb::ext_one(); r.d1 = kb::ext_one();
+    if (i < rows) {
+        const uint64_t s = (uint64_t)I * rows, o = base + (uint64_t)k * rows + i;
+        r.n0 = ldE(a, o); r.d0 = ldE(a, o + s); r.n1 = ldE(a, o + 2 * s); r.d1 = ldE(a, o + 3 * s);
+    }
+    return r;
+}
+__device__ __forceinline__ Row4 fix_rows(const Row4& x, const Row4& y, const Ext& a) {
+    Row4 r;
+    r.n0 = kb::ext_add(x.n0, kb::ext_mul(a, kb::ext_sub(y.n0, x.n0)));
+    r.d0 = kb::ext_add(x.d0, kb::ext_mul(a, kb::ext_sub(y.d0, x.d0)));
+    r.n1 = kb::ext_add(x.n1, kb::ext_mul(a, kb::ext_sub(y.n1, x.n1)));
+    r.d1 = kb::ext_add(x.d1, kb::ext_mul(a, kb::ext_sub(y.d1, x.d1)));
+    return r;
+}
+// contributions of the row pair (x = row 2i, y = row 2i+1) to (eval_0, eval_half, eq_sum)   logup_poly.rs:330-505
+__device__ __forceinline__ void pair_sums(const Row4& x, const Row4& y, const Ext& e, const Ext& er0, const Ext& er1, const Ext& lambda,
+                                          Ext& s0, Ext& sh, Ext& se) {
+    Ext t0 = kb::ext_add(kb::ext_mul(lambda, kb::ext_add(kb::ext_mul(x.d0, x.n1), kb::ext_mul(x.d1, x.n0))), kb::ext_mul(x.d0, x.d1));
+    Ext D0 = kb::ext_add(x.d0, y.d0), D1 = kb::ext_add(x.d1, y.d1), N0 = kb::ext_add(x.n0, y.n0), N1 = kb::ext_add(x.n1, y.n1);
+    Ext th = kb::ext_add(kb::ext_mul(lambda, kb::ext_add(kb::ext_mul(D0, N1), kb::ext_mul(D1, N0))), kb::ext_mul(D0, D1));
+    Ext ers = kb::ext_add(er0, er1);
+    s0 = kb::ext_add(s0, kb::ext_mul(kb::ext_mul(e, t0), er0));
+    sh = kb::ext_add(sh, kb::ext_mul(kb::ext_mul(e, th), ers));
+    se = kb::ext_add(se, kb::ext_mul(e, ers));
+}
+
+__device__ __forceinline__ void block_reduce3(Ext a, Ext b, Ext c, uint32_t* __restrict__ partial) {
+    __shared__ uint32_t red[12][256];
+    for (int l = 0; l < 4; l++) { red[l][threadIdx.x] = a.c[l]; red[4 + l][threadIdx.x] = b.c[l]; red[8 + l][threadIdx.x] = c.c[l]; }
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+            for (int l = 0; l < 12; l++) red[l][threadIdx.x] = kb::add(red[l][threadIdx.x], red[l][threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x < 12) partial[blockIdx.x * 12 + threadIdx.x] = red[threadIdx.x][0];
+}
+
+// round 0 of a layer: sums straight from the fraction sequence. work item = (chip, k, row pair i)
+__global__ void __launch_bounds__(256) gkr_sum_seq_kernel(JobTable jobs, const uint32_t* __restrict__ num, const uint32_t* __restrict__ den,
+                                                          const uint32_t* __restrict__ eq_int, const uint32_t* __restrict__ eq_row, Ext lambda,
+                                                          uint32_t* __restrict__ partial) {
+    Ext s0 = kb::ext_zero(), sh = kb::ext_zero(), se = kb::ext_zero();
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < jobs.total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const ChipJob& c = jobs.j[find_job(jobs, w)];
+        const uint64_t lw = w - c.work_start;
+        const uint32_t rows = (c.rows_in + 1) / 2, pairs = (rows + 1) / 2;
+        const uint32_t k = (uint32_t)(lw / pairs), i = (uint32_t)(lw - (uint64_t)k * pairs);
+        const uint64_t base = c.in_off + (uint64_t)k * c.rows_in;
+        Row4 x = row_from_seq(num, den, base, c.rows_in, 2 * i), y = row_from_seq(num, den, base, c.rows_in, 2 * i + 1);
+        pair_sums(x, y, ldE(eq_int, c.int_off + k), ldE(eq_row, 2 * i), ldE(eq_row, 2 * i + 1), lambda, s0, sh, se);
+    }
+    block_reduce3(s0, sh, se, partial);
+}
+
+// fix the last row variable (input = fraction sequence or working arrays), write the working arrays of the next round and
+// accumulate that round's sums.  work item = (chip, k, NEW row pair i): new rows 2i, 2i+1 come from old rows 4i .. 4i+3.
+template <bool FROM_SEQ>
+__global__ void __launch_bounds__(256) gkr_fix_sum_kernel(JobTable jobs, const uint32_t* __restrict__ in_a, const uint32_t* __restrict__ in_b,
+                                                          uint32_t* __restrict__ out, const uint32_t* __restrict__ eq_int,
+                                                          const uint32_t* __restrict__ eq_row_new, Ext alpha, Ext lambda, uint32_t* __restrict__ partial) {
+    Ext s0 = kb::ext_zero(), sh = kb::ext_zero(), se = kb::ext_zero();
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < jobs.total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const ChipJob& c = jobs.j[find_job(jobs, w)];
+        const uint64_t lw = w - c.work_start;
+        const uint32_t rows_old = FROM_SEQ ? (c.rows_in + 1) / 2 : c.rows_in;
+        const uint32_t rows_new = (rows_old + 1) / 2, pairs = (rows_new + 1) / 2;
+        const uint32_t k = (uint32_t)(lw / pairs), i = (uint32_t)(lw - (uint64_t)k * pairs);
+        Row4 nr[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const uint32_t o = 2 * i + hh;  // new row index; old rows 2o, 2o+1
+            Row4 x, y;
+            if (FROM_SEQ) {
+                const uint64_t base = c.in_off + (uint64_t)k * c.rows_in;
+                x = row_from_seq(in_a, in_b, base, c.rows_in, 2 * o); y = row_from_seq(in_a, in_b, base, c.rows_in, 2 * o + 1);
+            } else {
+                x = row_from_work(in_a, c.in_off, c.I, rows_old, k, 2 * o); y = row_from_work(in_a, c.in_off, c.I, rows_old, k, 2 * o + 1);
+            }
+            nr[hh] = fix_rows(x, y, alpha);
+            if (o < rows_new) {
+                const uint64_t s = (uint64_t)c.I * rows_new, q = c.out_off + (uint64_t)k * rows_new + o;
+                stE(out, q, nr[hh].n0); stE(out, q + s, nr[hh].d0); stE(out, q + 2 * s, nr[hh].n1); stE(out, q + 3 * s, nr[hh].d1);
+            } else {  // beyond the real rows: padding values for the sums below
+                nr[hh].n0 = kb::ext_zero(); nr[hh].n1 = kb::ext_zero(); nr[hh].d0 = kb::ext_one(); nr[hh].d1 = kb::ext_one();
+            }
+        }
+        pair_sums(nr[0], nr[1], ldE(eq_int, c.int_off + k), ldE(eq_row_new, 2 * i), ldE(eq_row_new, 2 * i + 1), lambda, s0, sh, se);
+    }
+    block_reduce3(s0, sh, se, partial);
+}
+
+__global__ void gkr_eq_table_kernel(const uint32_t* __restrict__ point, int k, uint32_t* __restrict__ E) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ((uint64_t)1 << k)) return;
+    Ext acc = kb::ext_one();
+    for (int t = 0; t < k; t++) {
+        Ext x = kb::ext_load(point + 4 * t);
+        bool bit = (j >> (k - 1 - t)) & 1;
+        acc = kb::ext_mul(acc, bit ? x : kb::ext_sub(kb::ext_one(), x));
+    }
+    kb::ext_store(E + 4 * j, acc);
+}
+// E'[j] = E[2j] + alpha (E[2j+1] - E[2j])
+__global__ void gkr_fix_eq_kernel(const uint32_t* __restrict__ E, uint64_t n_out, Ext alpha, uint32_t* __restrict__ Eo) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    Ext a = ldE(E, 2 * j), b = ldE(E, 2 * j + 1);
+    stE(Eo, j, kb::ext_add(a, kb::ext_mul(alpha, kb::ext_sub(b, a))));
+}
+// per-column openings: out[c] = sum_{r < rows} eq[r] * col[r]
+__global__ void __launch_bounds__(256) gkr_column_open_kernel(const uint32_t* __restrict__ cols, uint64_t h, const uint32_t* __restrict__ eq,
+                                                              uint32_t* __restrict__ out) {
+    const uint64_t c = blockIdx.x;
+    const uint32_t* col = cols + c * h;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (uint64_t i = threadIdx.x; i < h; i += blockDim.x) {
+        uint32_t x = __ldg(col + i);
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(eq + 4 * i));
+        a0 = kb::add(a0, kb::mul(x, v.x)); a1 = kb::add(a1, kb::mul(x, v.y));
+        a2 = kb::add(a2, kb::mul(x, v.z)); a3 = kb::add(a3, kb::mul(x, v.w));
+    }
+    __shared__ uint32_t red[4][256];
+    red[0][threadIdx.x] = a0; red[1][threadIdx.x] = a1; red[2][threadIdx.x] = a2; red[3][threadIdx.x] = a3;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+            for (int l = 0; l < 4; l++) red[l][threadIdx.x] = kb::add(red[l][threadIdx.x], red[l][threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) out[c * 4 + threadIdx.x] = red[threadIdx.x][0];
+}
+
+struct DevFree {
+    sp1b200_ctx* ctx; std::vector<void*> ptrs;
+    explicit DevFree(sp1b200_ctx* c) : ctx(c) {}
+    ~DevFree() { for (void* p : ptrs) cudaFreeAsync(p, ctx->stream); }
+    sp1b200_err alloc(void** p, size_t bytes) { SP1_CUDA(cudaMallocAsync(p, bytes ? bytes : 4, ctx->stream)); ptrs.push_back(*p); return nullptr; }
+};
+inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+std::vector<E4> host_interp(const std::vector<E4>& xs, const std::vector<E4>& ys) {
+    size_t n = xs.size();
+    std::vector<E4> res(n);
+    for (size_t i = 0; i < n; i++) {
+        std::vector<E4> num{ys[i]};
+        E4 den = E4::one();
+        for (size_t j = 0; j < n; j++) {
+            if (j == i) continue;
+            den = den * (xs[i] - xs[j]);
+            std::vector<E4> nx(num.size() + 1);
+            for (size_t k = 0; k < num.size(); k++) { nx[k + 1] = nx[k + 1] + num[k]; nx[k] = nx[k] - num[k] * xs[j]; }
+            num.swap(nx);
+        }
+        E4 dinv = hf::inv(den);
+        for (size_t k = 0; k < num.size(); k++) res[k] = res[k] + num[k] * dinv;
+    }
+    return res;
+}
+E4 host_poly_eval(const std::vector<E4>& c, const E4& x) { E4 r; for (size_t i = c.size(); i-- > 0;) r = r * x + c[i]; return r; }
+inline Ext toExt(const E4& e) { return Ext{{e.c[0], e.c[1], e.c[2], e.c[3]}}; }
+
+const uint32_t* parse_vcol(const uint32_t* b, HostInteractions& H) {
+    VColDev v; v.n_terms = *b++; v.constant = *b++; v.term_start = (uint32_t)H.terms.size();
+    for (uint32_t i = 0; i < v.n_terms; i++) { H.terms.push_back(TermDev{b[0], b[1], b[2]}); b += 3; }
+    H.vcols.push_back(v);
+    return b;
+}
+
+}  // namespace
+
+// parses the interaction section that follows the AIR records in the machine blob (called by sp1b200_machine_create)
+void* sp1b200_parse_interactions(const uint32_t* b, const uint32_t* end, size_t n_chips) {
+    auto H = std::make_unique<HostInteractions>();
+    H->per_chip.resize(n_chips);
+    if (b >= end) return H.release();  // machine without interactions (zerocheck-only tests)
+    for (auto& chip : H->per_chip) {
+        uint32_t n = *b++;
+        for (uint32_t i = 0; i < n; i++) {
+            InterDev in; in.is_send = *b++; in.arg_index = *b++; in.n_values = *b++; in.vcol_start = (uint32_t)H->vcols.size();
+            b = parse_vcol(b, *H);
+            for (uint32_t k = 0; k < in.n_values; k++) b = parse_vcol(b, *H);
+            chip.push_back(in);
+        }
+    }
+    return H.release();
+}
+void sp1b200_free_interactions(void* p) { delete static_cast<HostInteractions*>(p); }
+
+extern "C" {
+
+// GkrProverImpl::prove_logup_gkr (crates/hypercube/src/logup_gkr/prover.rs:70-215).
+// d_main[k]/d_prep[k]: chip columns (column-major [w x h_heights[k]]), interactions from the machine blob.
+// h_replay_witness: the GKR grinding witness when params.grind_mode == 1.
+// Output words: n_out | numerator[n_out] ext | denominator[n_out] ext | n_rounds | per round {numerator_0, numerator_1,
+//   denominator_0, denominator_1 ext, sumcheck {n_polys, per poly {n_coeffs, coeffs}, claimed_sum, point, eval}} |
+//   evaluation point (max_log_row_count ext) | per chip {main openings, preprocessed openings} | witness
+sp1b200_err sp1b200_logup_gkr(sp1b200_ctx* ctx, const sp1b200_machine* m, const uint64_t* h_heights, const uint32_t* const* d_main,
+                              const uint32_t* const* d_prep, const uint32_t* h_replay_witness, uint32_t* h_chal, uint32_t* h_out, uint64_t cap,
+                              uint64_t* h_words);
+
+}
+
+#include "gkr_driver.inc"

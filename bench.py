@@ -25,9 +25,11 @@ sys.path.insert(0, ROOT)
 
 from sp1_b200 import workload as W  # noqa: E402
 
-PHASES_DONE = ["commit(main): rs_encode + poseidon2 merkle", "jagged open: hadamard sumcheck + branching-program sumcheck",
+PHASES_DONE = ["commit(main): rs_encode + poseidon2 merkle", "logup-gkr: grind(12) + fraction circuit + 21 layer sumchecks + openings",
+               "zerocheck: constraint bytecode interpreter, 22 rounds over all chips",
+               "jagged open: hadamard sumcheck + branching-program sumcheck",
                "stacked/basefold open: batch + 21 fold rounds + 2 grinds + 124 queries"]
-PHASES_MISSING = ["logup-gkr", "zerocheck"]  # column claims are produced by a direct evaluation kernel instead
+PHASES_MISSING = []  # the step is the whole prove_shard_with_data body (shard.rs:650-792) on synthetic AIRs
 
 
 def peaks():
@@ -79,34 +81,32 @@ class ClockSampler:
 
 
 def cpu_baseline(workload_name, target_seconds=20.0):
-    """The oracle port (oracle/liboracle.so, OpenMP over the host cores) on a BOUNDED sample of the same workload:
-    a shard of the same chip mix scaled down so that commit + open take about target_seconds."""
+    """The oracle port (oracle/liboracle.so, OpenMP over the host cores) proving a BOUNDED sample of the same workload:
+    the same synthetic machine with every chip height scaled down (whole prove_shard body, verifier skipped)."""
     from tests import oracle_lib as O
+    from sp1_b200 import synth_air as SA
     L = O.lib()
     cores = L.orc_num_threads()
-    sample_area = 1 << 23
-    prep, main = W.shard_shapes(workload_name, seed=42)
-    scale = sample_area / W.area_of(main)
-    main_s = [(max(int(r * scale) // 32 * 32, 32) if r else 0, c) for r, c in main]
-    prep_s = [(max(int(r * scale) // 32 * 32, 32), c) for r, c in prep]
+    full = W.synthetic_machine(workload_name, seed=42)
+    scale = (1 << 22) / W.area_of(full["main_shapes"])
+    mach = W.synthetic_machine(workload_name, seed=42, scale=scale)
     rng = np.random.default_rng(7)
-    rounds = [O.random_tables(rng, prep_s), O.random_tables(rng, main_s)]
-    z_row = O.rand_field(rng, (22, 4))
+    mains, preps = [], []
+    for h, g, wp in mach["specs"]:
+        m_, p_ = SA.synth_trace(rng, h, g, wp, 12345)
+        mains.append(m_); preps.append(p_)
+    pv = O.to_monty(np.array([12345, 5, 6, 7]))
     ch = O.Challenger()
     L.orc_set_skip_verify(1)
     t0 = time.time()
-    O.jagged_prove_verify(rounds, 21, 22, z_row, ch)
+    O.prove_shard_verify(mach["blob"], [h for h, _, _ in mach["specs"]], mains, preps, mach["names"], pv, 21, 22, ch)
     wall = time.time() - t0
     L.orc_set_skip_verify(0)
-    import ctypes as C
-    times = (C.c_double * 4)()
-    L.orc_last_times(times)
-    step_s = times[2] + times[3]           # main-round commit + open (the prep commit is setup, as on the GPU arm)
-    cells = W.area_of(main_s)
-    return {"value": cells / W.CELLS_PER_CYCLE / step_s, "unit": "cycles/s", "cores": int(cores), "kind": "port",
-            "sample": f"same chip mix scaled to {cells} cells ({cells / W.CELLS_PER_CYCLE:.0f} cycles): main commit "
-                      f"{times[2]:.2f}s + open {times[3]:.2f}s (wall incl. claims+prep {wall:.1f}s), "
-                      "oracle C++ port with OpenMP — not the Rust/AVX-512 Plonky3 prover (cargo absent)"}
+    cells = W.area_of(mach["main_shapes"])
+    return {"value": cells / W.CELLS_PER_CYCLE / wall, "unit": "cycles/s", "cores": int(cores), "kind": "port",
+            "sample": f"same machine, heights scaled to {cells} main cells ({cells / W.CELLS_PER_CYCLE:.0f} cycles): whole shard proof "
+                      f"(setup commit + prove_shard body) in {wall:.1f}s; oracle C++ port with OpenMP - not the Rust/AVX-512 "
+                      "Plonky3 prover (cargo absent in this image)"}
 
 
 def run_reference(args):
@@ -157,41 +157,46 @@ def main():
     lib = Lib(device=local)
     stream = torch.cuda.ExternalStream(lib.stream(), device=dev)
 
-    prep, main_shapes = W.shard_shapes(args.workload, seed=42 + rank)
-    cells = W.area_of(main_shapes)
+    from sp1_b200 import synth_air as SA
+    mach = W.synthetic_machine(args.workload, seed=42 + rank)
+    specs, names = mach["specs"], mach["names"]
+    heights = [h for h, _, _ in specs]
+    cells = W.area_of(mach["main_shapes"])
     cycles = cells / W.CELLS_PER_CYCLE
-    rows_m, cols_m = [r for r, _ in main_shapes], [c for _, c in main_shapes]
-    rows_p, cols_p = [r for r, _ in prep], [c for _, c in prep]
-    ncols_main, ncols_prep = sum(cols_m), sum(cols_p)
-    d_prep = W.random_dense_cuda(prep, 1000 + rank, dev)
-    d_main = W.random_dense_cuda(main_shapes, 2000 + rank, dev)
+    pv0 = 12345
+    pv = ((np.array([pv0, 5, 6, 7], dtype=np.uint64) << np.uint64(32)) % np.uint64(W.P)).astype(np.uint32)
+    mains, preps = [], []
+    for i, (h, g, wp) in enumerate(specs):
+        m_, p_ = SA.synth_trace_cuda(h, g, wp, pv0, 1000 * (rank + 1) + i, dev)
+        mains.append(m_)
+        if wp:
+            preps.append(p_)
+    d_main = torch.cat(mains).contiguous()
+    d_prep = torch.cat(preps).contiguous()
+    del mains, preps
     h_main = torch.empty(d_main.shape, dtype=torch.int32, pin_memory=True)
     h_main.copy_(d_main)
     torch.cuda.synchronize()
-    # setup (not timed, reference: AirProver::setup commits the preprocessed traces once per program)
-    _, h_prep = lib.jagged_commit_dense(d_prep, rows_p, cols_p)
-    rng = np.random.default_rng(5)
-    z_row = rng.integers(0, W.P, size=(22, 4), dtype=np.uint32)
-    claims_prep = lib.jagged_column_claims(h_prep, z_row, ncols_prep)
-    chal0 = np.zeros(34, np.uint32)
+    # setup (not timed; reference: AirProver::setup uploads the machine and commits the preprocessed traces once per program)
+    machine = lib.machine_create(mach["blob"])
+    prep_rows = [h for h, _, wp in specs if wp]
+    _, h_prep = lib.jagged_commit_dense(d_prep, prep_rows, [1] * len(prep_rows))
+    chal0 = HostChallenger().st.copy()
+    padded_cells = ((cells + (1 << 21) - 1) >> 21) << 21
 
-    phase_names = ["commit.rs_encode", "commit.merkle", "jagged.little_poly", "jagged.sumcheck", "jagged.eval_sumcheck", "open.batch",
-                   "open.fri_rounds", "open.queries", "open.total", "jagged.total"]
+    phase_names = ["commit.rs_encode", "commit.merkle", "shard.commit", "gkr.circuit", "gkr.rounds", "gkr.openings", "gkr.total",
+                   "zerocheck.total", "jagged.little_poly", "jagged.sumcheck", "jagged.eval_sumcheck", "open.batch", "open.fri_rounds",
+                   "open.queries", "open.total", "jagged.total", "shard.total"]
     acc = {}
 
     def step(src, record=False):
-        commit, h = lib.jagged_commit_dense(src, rows_m, cols_m)
+        st = chal0.copy()
+        proof = lib.prove_shard(machine, h_prep, src, heights, names, pv, st)
         if record:
-            for n in ("commit.rs_encode", "commit.merkle"):
-                acc[n] = acc.get(n, 0.0) + lib.phase_ms(n)
-        claims_main = lib.jagged_column_claims(h, z_row, ncols_main)  # stand-in for the zerocheck openings (see PHASES_MISSING)
-        ch = HostChallenger(chal0)
-        ch.observe(commit)
-        proof = lib.jagged_prove([h_prep, h], z_row, np.concatenate([claims_prep, claims_main]), ch.st)
-        if record:
-            for n in phase_names[2:]:
-                acc[n] = acc.get(n, 0.0) + lib.phase_ms(n)
-        lib.jagged_round_free(h)
+            for n in phase_names:
+                v = lib.phase_ms(n)
+                if v >= 0:
+                    acc[n] = acc.get(n, 0.0) + v
         return proof
 
     def timed(src, k):
@@ -233,16 +238,15 @@ def main():
     e2e = total_cycles * args.steps / (ms_e2e / 1e3)
     hbm, peak_src = peaks()
     ntt_ms = phases.get("commit.rs_encode", float("nan"))
-    padded_cells = ((cells + (1 << 21) - 1) >> 21) << 21
     ach = 20.0 * padded_cells / (ntt_ms / 1e3) / 1e9
     merkle_ms = phases.get("commit.merkle", float("nan"))
-    perms = (1 << 23) * ((padded_cells >> 21) + 7) // 8 + (1 << 23)
+    perms = (1 << 23) * (((padded_cells >> 21) + 7) // 8) + (1 << 23)
     out = {
         "metric": "riscv_cycles_proven_per_second_core", "value": value, "unit": "cycles/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 KoalaBear (Montgomery) / ext4", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {W.WORKLOADS[args.workload][1]}; main area {cells} cells = {cycles:.0f} cycles/shard "
-                               f"(cells/45), {len(main_shapes)} chips, {padded_cells >> 21} stacked columns of 2^21, blowup 4, "
+                               f"(cells/45), {len(specs)} chips (synthetic AIR bytecode + LogUp interactions), {padded_cells >> 21} stacked columns of 2^21, blowup 4, "
                                "124 queries, 16+5 PoW bits; one shard per GPU per step",
                    "phases": PHASES_DONE, "phases_not_yet_in_step": PHASES_MISSING,
                    "l2": "working set (>= 3 GB codeword per shard) exceeds the 126 MB L2 between iterations"},
@@ -266,6 +270,7 @@ def main():
                 out["cpu_baseline"] = {"value": None, "unit": "cycles/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(out))
     lib.jagged_round_free(h_prep)
+    lib.machine_free(machine)
     lib.close()
     if world > 1:
         dist.destroy_process_group()

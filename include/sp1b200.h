@@ -204,6 +204,26 @@ sp1b200_err sp1b200_logup_gkr(sp1b200_ctx* ctx, const sp1b200_machine* machine, 
                               const uint32_t* const* d_main, const uint32_t* const* d_prep, const uint32_t* h_replay_witness,
                               uint32_t* h_challenger34, uint32_t* h_out, uint64_t out_cap_words, uint64_t* h_out_words);
 
+/* ---- whole shard (the AirProver::prove_shard_with_pk body; replaces CudaShardProver::prove_shard_with_data,
+ *      sp1-gpu/crates/shard_prover/src/prover.rs:618-763) -------------------------------------------------------------- */
+
+/* ShardProver::prove_shard_with_data (crates/hypercube/src/prover/shard.rs:650-792): observe public values, commit the main
+ * traces, observe the commitment and every chip's (height, name), LogUp-GKR, sample alpha and gamma, zerocheck, jagged
+ * evaluation proof at the zerocheck point over {preprocessed round, main round}.
+ * machine: chips in BTreeSet (name) order; prep_round: the preprocessed commitment made at setup with
+ * sp1b200_jagged_commit over the chips with preprocessed columns (NULL if the machine has none; heights must equal the
+ * main heights, as the reference verifier requires, verifier/shard.rs:690-720); main_dense_any: main tables back to back
+ * (TraceDenseData layout); chip_names: NUL-terminated names in chip order; h_challenger34: the transcript after the
+ * verifying key has been observed (crates/hypercube/src/verifier/config.rs:97-112), updated in place.
+ * h_replay_witnesses (grind_mode == 1): {gkr, batch grinding, pow}.
+ * Proof words: [5][len_0..len_4] then  main commitment (8) | LogUp-GKR (sp1b200_logup_gkr words) | zerocheck + opened values
+ * (sp1b200_zerocheck words) | evaluation proof (sp1b200_jagged_prove words) | public values
+ * = the fields of ShardProof (crates/hypercube/src/verifier/proof.rs:47-61). */
+sp1b200_err sp1b200_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* machine, sp1b200_jagged_round* prep_round,
+                                const uint32_t* main_dense_any, const uint64_t* h_heights, const char* const* chip_names,
+                                const uint32_t* h_public_values, uint32_t n_public_values, const uint32_t* h_replay_witnesses,
+                                uint32_t* h_challenger34, uint32_t* h_proof, uint64_t proof_cap_words, uint64_t* h_proof_words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -386,4 +386,102 @@ int64_t orc_gkr_prove_verify(const uint32_t* machine_blob, const uint64_t* heigh
     return (int64_t)o.size();
 }
 
+
+// ---- whole shard: ShardProver::prove_shard_with_data (crates/hypercube/src/prover/shard.rs:650-792) + the restated
+// ShardVerifier::verify_shard (crates/hypercube/src/verifier/shard.rs:437-750; machine-shape / cluster checks that depend on the
+// Rust machine definition are out of scope).  prep_dense: preprocessed tables of the chips with prep_w > 0 back to back
+// (column-major each); main_dense: main tables of all chips.  names: chip names separated by '\0'.
+// Words out: [5][len_0..len_4] | main commitment | gkr | zerocheck (+ opened values) | evaluation proof | public values.
+int64_t orc_prove_shard_verify(const uint32_t* machine_blob, const uint64_t* heights, const uint32_t* prep_dense, const uint32_t* main_dense,
+                               const char* names, const uint32_t* pv_words, uint32_t n_pv, uint32_t log_stack, uint32_t max_log_rows,
+                               uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits, uint32_t batch_pow_bits, uint32_t gkr_pow_bits,
+                               uint32_t* challenger_state, uint32_t* prep_commit_out, uint32_t* out, uint64_t cap) {
+    FriParams fp; fp.log_blowup = log_blowup; fp.num_queries = num_queries; fp.pow_bits = pow_bits; fp.batch_pow_bits = batch_pow_bits;
+    const uint32_t* rest;
+    std::vector<MachineChip> mc = parse_machine(machine_blob, &rest);
+    auto inter = parse_interactions(rest, mc.size());
+    const size_t n = mc.size();
+    std::vector<std::string> nm;
+    { const char* p = names; for (size_t k = 0; k < n; k++) { nm.emplace_back(p); p += nm.back().size() + 1; } }
+    std::vector<F> pv(n_pv);
+    for (uint32_t i = 0; i < n_pv; i++) pv[i] = F::raw(pv_words[i]);
+    // tables
+    std::vector<Table> ptabs, mtabs;
+    std::vector<GkrChip> gchips(n);
+    std::vector<ZcChip> zchips(n);
+    const F* pp = asF(prep_dense); const F* mp = asF(main_dense);
+    for (size_t k = 0; k < n; k++) {
+        Table t; t.rows = heights[k]; t.cols = mc[k].main_w; t.data = mp; mtabs.push_back(t);
+        gchips[k].height = heights[k]; gchips[k].main_w = mc[k].main_w; gchips[k].prep_w = mc[k].prep_w; gchips[k].main = mp; gchips[k].inter = inter[k];
+        zchips[k].air = &mc[k].air; zchips[k].height = heights[k]; zchips[k].main_w = mc[k].main_w; zchips[k].prep_w = mc[k].prep_w; zchips[k].main = mp;
+        mp += heights[k] * mc[k].main_w;
+        if (mc[k].prep_w) {
+            Table p; p.rows = heights[k]; p.cols = mc[k].prep_w; p.data = pp; ptabs.push_back(p);
+            gchips[k].prep = pp; zchips[k].prep = pp;
+            pp += heights[k] * mc[k].prep_w;
+        }
+    }
+    const bool has_prep = !ptabs.empty();
+    // setup: preprocessed commit (AirProver::setup, shard.rs:406-429)
+    JaggedRound prep_round;
+    if (has_prep) { prep_round = jagged_commit(ptabs, log_stack, max_log_rows, fp); for (int i = 0; i < 8; i++) prep_commit_out[i] = prep_round.commit.d[i].v; }
+    Challenger ch; chal_load(ch, challenger_state);
+    Challenger vch = ch;
+    // ---- prove
+    ch.observe_slice(pv.data(), pv.size());
+    JaggedRound main_round = jagged_commit(mtabs, log_stack, max_log_rows, fp);
+    ch.observe(main_round.commit);
+    ch.observe(F::from_canonical(n));
+    for (size_t k = 0; k < n; k++) {
+        ch.observe(F::from_canonical(heights[k])); ch.observe(F::from_canonical(nm[k].size()));
+        for (unsigned char b : nm[k]) ch.observe(F::from_canonical(b));
+    }
+    GkrProof gp = gkr_prove(gchips, max_log_rows, gkr_pow_bits, ch);
+    EF alpha = ch.sample_ext(), gamma = ch.sample_ext();
+    std::vector<EF> claims(n);
+    for (size_t k = 0; k < n; k++) {
+        EF g = gamma, a;
+        for (auto& e : gp.main_open[k]) { a += e * g; g *= gamma; }
+        for (auto& e : gp.prep_open[k]) { a += e * g; g *= gamma; }
+        claims[k] = a;
+    }
+    ZerocheckResult zr = zerocheck_prove(zchips, alpha, gamma, gp.point, claims, pv, max_log_rows, ch);
+    std::vector<JaggedRound> rounds;
+    std::vector<std::vector<EF>> jclaims;
+    if (has_prep) { rounds.push_back(prep_round); std::vector<EF> c; for (auto& o : zr.opened) c.insert(c.end(), o.prep.begin(), o.prep.end()); jclaims.push_back(c); }
+    { rounds.push_back(main_round); std::vector<EF> c; for (auto& o : zr.opened) c.insert(c.end(), o.main.begin(), o.main.end()); jclaims.push_back(c); }
+    JaggedProof jp = jagged_prove(zr.proof.point, jclaims, rounds, max_log_rows, ch, fp);
+    chal_store(ch, challenger_state);
+    // ---- verify (verify_shard order)
+    if (!g_skip_verify) {
+        vch.observe_slice(pv.data(), pv.size());
+        vch.observe(main_round.commit);
+        vch.observe(F::from_canonical(n));
+        for (size_t k = 0; k < n; k++) {
+            vch.observe(F::from_canonical(heights[k])); vch.observe(F::from_canonical(nm[k].size()));
+            for (unsigned char b : nm[k]) vch.observe(F::from_canonical(b));
+        }
+        const char* err = gkr_verify(gchips, max_log_rows, gkr_pow_bits, gp, vch);
+        if (!err) err = zerocheck_verify(zchips, zr.opened, gp.point, gp.main_open, gp.prep_open, zr.proof, pv, max_log_rows, vch);
+        if (!err) {
+            std::vector<Digest> commits;
+            if (has_prep) commits.push_back(prep_round.commit);
+            commits.push_back(main_round.commit);
+            err = jagged_verify(commits, zr.proof.point, jclaims, jp, vch, log_stack, max_log_rows, fp);
+        }
+        if (err) { std::fprintf(stderr, "oracle shard verifier rejected oracle proof: %s\n", err); return -1; }
+    }
+    std::vector<uint32_t> s0, s1, s2, s3;
+    put(s0, main_round.commit);
+    put(s1, gp);
+    put(s2, zr.proof);
+    for (auto& c : zr.opened) { for (auto& e : c.prep) put(s2, e); for (auto& e : c.main) put(s2, e); }
+    put(s3, jp);
+    std::vector<uint32_t> o{5, (uint32_t)s0.size(), (uint32_t)s1.size(), (uint32_t)s2.size(), (uint32_t)s3.size(), n_pv};
+    o.insert(o.end(), s0.begin(), s0.end()); o.insert(o.end(), s1.begin(), s1.end()); o.insert(o.end(), s2.begin(), s2.end());
+    o.insert(o.end(), s3.begin(), s3.end()); o.insert(o.end(), pv_words, pv_words + n_pv);
+    if (out) { if (o.size() > cap) return -2; std::copy(o.begin(), o.end(), out); }
+    return (int64_t)o.size();
+}
+
 }  // extern "C"

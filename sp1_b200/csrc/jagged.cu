@@ -23,13 +23,7 @@ extern "C" sp1b200_err sp1b200_stacked_prove(sp1b200_ctx*, sp1b200_commit* const
                                              uint32_t*, uint32_t*, uint64_t, uint64_t*);
 void host_poseidon2_permute(uint32_t* s16);
 
-struct sp1b200_jagged_round {
-    sp1b200_commit* stacked = nullptr;
-    std::vector<uint64_t> row_counts, col_counts;  // including the two dummy tables
-    uint64_t padding_cols = 0, area = 0, padded_area = 0;
-    uint32_t* d_dense = nullptr;  // owned, padded_area words
-    uint32_t original_commit[8], commit[8];
-};
+#include "pcs.cuh"
 
 namespace {
 

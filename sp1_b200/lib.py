@@ -56,7 +56,7 @@ ERR_FUNCS = [
     "sp1b200_ctx_create", "sp1b200_ctx_sync", "sp1b200_malloc", "sp1b200_free", "sp1b200_memcpy_h2d",
     "sp1b200_memcpy_d2h", "sp1b200_poseidon2_permute", "sp1b200_rs_encode", "sp1b200_merkle_commit", "sp1b200_grind",
     "sp1b200_stacked_commit", "sp1b200_stacked_prove", "sp1b200_jagged_commit", "sp1b200_jagged_column_claims",
-    "sp1b200_jagged_prove", "sp1b200_machine_create", "sp1b200_zerocheck", "sp1b200_logup_gkr",
+    "sp1b200_jagged_prove", "sp1b200_machine_create", "sp1b200_zerocheck", "sp1b200_logup_gkr", "sp1b200_prove_shard",
 ]
 OTHER_FUNCS = ["sp1b200_challenger_init", "sp1b200_challenger_observe", "sp1b200_challenger_sample",
                "sp1b200_challenger_sample_bits", "sp1b200_challenger_check_witness", "sp1b200_ctx_destroy", "sp1b200_default_core_params", "sp1b200_version", "sp1b200_ctx_stream",
@@ -240,6 +240,18 @@ class Lib:
         rw = None if replay is None else np.ascontiguousarray([replay], dtype=np.uint32)
         self._chk(self.L.sp1b200_logup_gkr(self.ctx, machine, H, M, Pp, _ptr(rw), _ptr(challenger_state), _ptr(out),
                                            C.c_uint64(cap_words), C.byref(nw)))
+        return out[:nw.value].copy()
+
+    def prove_shard(self, machine, prep_round, main_dense, heights, names, pv, challenger_state, replay=None, cap_words=1 << 24):
+        n = len(heights)
+        H = (C.c_uint64 * n)(*heights)
+        NM = (C.c_char_p * n)(*[s.encode() for s in names])
+        pv = np.ascontiguousarray(pv, dtype=np.uint32)
+        out = np.zeros(cap_words, np.uint32)
+        nw = C.c_uint64()
+        rw = None if replay is None else np.ascontiguousarray(replay, dtype=np.uint32)
+        self._chk(self.L.sp1b200_prove_shard(self.ctx, machine, prep_round, _ptr(main_dense), H, NM, _ptr(pv), C.c_uint32(pv.size),
+                                             _ptr(rw), _ptr(challenger_state), _ptr(out), C.c_uint64(cap_words), C.byref(nw)))
         return out[:nw.value].copy()
 
     def grind(self, state34, bits):

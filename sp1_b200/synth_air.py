@@ -133,12 +133,13 @@ def _vcol(terms, constant=0):
     return w
 
 
-def synth_interactions(groups, with_prep):
+def synth_interactions(groups, with_prep, inter_groups=None):
     """Balanced sends/receives for a synth_chip: every tuple that is sent is received with the same multiplicity, so the
     cumulative LogUp sum is zero.  Words for one chip: n_interactions then per interaction
     is_send arg_index n_values, multiplicity vcol, value vcols."""
     inter = []
-    for g in range(groups):
+    ig = groups if inter_groups is None else max(1, min(groups, inter_groups))
+    for g in range(ig):
         base = 6 * g
         a, b, c, d, e, f = (base + i for i in range(6))
         vals3 = [_vcol([(LEAF_MAIN, a, 1)]), _vcol([(LEAF_MAIN, b, 1), (LEAF_MAIN, a, 2)]), _vcol([(LEAF_MAIN, c, 1)], constant=5)]
@@ -146,7 +147,7 @@ def synth_interactions(groups, with_prep):
         inter.append((1, 5, mult_d, vals3))                     # send, kind Byte(5), multiplicity d
         vals1 = [_vcol([(LEAF_MAIN, e, 3)])]
         inter.append((1, 7, _vcol([], constant=1), vals1))      # send, kind State(7), multiplicity 1
-    for g in range(groups):
+    for g in range(ig):
         base = 6 * g
         a, b, c, d, e, f = (base + i for i in range(6))
         vals3 = [_vcol([(LEAF_MAIN, a, 1)]), _vcol([(LEAF_MAIN, a, 2), (LEAF_MAIN, b, 1)]), _vcol([(LEAF_MAIN, c, 1)], constant=5)]
@@ -154,7 +155,7 @@ def synth_interactions(groups, with_prep):
         inter.append((0, 7, _vcol([], constant=1), [_vcol([(LEAF_MAIN, e, 3)])]))
     if with_prep:
         gv = [_vcol([(LEAF_PREP, 0, 1)]), _vcol([(LEAF_MAIN, 6 * groups, 1)])]
-        inter.insert(2 * groups, (1, 2, _vcol([(LEAF_MAIN, 3, 1)]), gv))   # send (g, h) with multiplicity d0
+        inter.insert(2 * ig, (1, 2, _vcol([(LEAF_MAIN, 3, 1)]), gv))   # send (g, h) with multiplicity d0
         inter.append((0, 2, _vcol([(LEAF_MAIN, 3, 1)]), gv))
     w = [len(inter)]
     for is_send, kind, mult, vals in inter:
@@ -171,3 +172,36 @@ def machine_blob_with_interactions(chip_words, inter_words):
     for iw in inter_words:
         w += iw
     return np.array(w, dtype=np.uint32)
+
+
+def synth_trace_cuda(height, groups, with_prep, pv0_canonical, seed, device, kconst=7):
+    """same trace family generated on the GPU with torch (bench input only): -> (main [w*height] int32 Montgomery words
+    column-major, prep [height] or None)"""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    w = 6 * groups + (1 if with_prep else 0)
+    if height == 0:
+        return torch.zeros(0, dtype=torch.int32, device=device), (torch.zeros(0, dtype=torch.int32, device=device) if with_prep else None)
+    out = torch.empty((w, height), dtype=torch.int32, device=device)
+
+    def mont(x):  # canonical int64 -> Montgomery word
+        return ((x << 32) % P).to(torch.int32)
+    a0 = None
+    for gi in range(groups):
+        a = torch.randint(0, P, (height,), dtype=torch.int64, device=device, generator=g)
+        b = torch.randint(0, P, (height,), dtype=torch.int64, device=device, generator=g)
+        d = torch.randint(0, 2, (height,), dtype=torch.int64, device=device, generator=g)
+        c = a * b % P
+        e = c * d % P
+        f = (a + kconst * pv0_canonical) % P
+        for i, col in enumerate((a, b, c, d, e, f)):
+            out[6 * gi + i] = mont(col)
+        if gi == 0:
+            a0 = a
+    prep = None
+    if with_prep:
+        gc = torch.randint(0, P, (height,), dtype=torch.int64, device=device, generator=g)
+        out[6 * groups] = mont(gc * a0 % P)
+        prep = mont(gc)
+    return out.reshape(-1), prep

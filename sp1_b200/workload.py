@@ -76,3 +76,32 @@ def random_dense_cuda(shapes, seed, device):
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     return torch.randint(0, P, (area_of(shapes),), dtype=torch.int32, device=device, generator=g)
+
+
+# ---- full-shard synthetic machine (constraints + interactions) for bench.py and the scale tests -------------------------------
+def synthetic_machine(workload, seed=42, max_log_rows=22, scale=1.0):
+    """-> dict(names, specs [(height, groups, with_prep)], blob, main_shapes [(rows, cols)], prep_shapes)
+    chips = the core cluster's chips (CORE_CHIPS widths -> 6-column constraint groups) + the three preprocessed tables,
+    in name order; heights from shard_shapes (multiples of 32), optionally scaled down by `scale` (CPU baseline sample)."""
+    from . import synth_air as SA
+    prep, main = shard_shapes(workload, seed=seed, max_log_rows=max_log_rows)
+    chips = sorted(CORE_CHIPS)
+    entries = []
+    for (name, w), (rows, _) in zip(chips, main):
+        entries.append((name, max(1, round(w / 6)), False, rows))
+    for (name, w, _), (rows, _) in zip(sorted(PREP_CHIPS), prep):
+        entries.append((name, max(1, round(w / 6)), True, rows))
+    entries.sort(key=lambda e: e[0])
+    names, specs, words, iwords = [], [], [], []
+    for name, g, wp, rows in entries:
+        h = int(rows * scale) // 32 * 32 if rows else 0
+        if rows and not h:
+            h = 32
+        names.append(name); specs.append((h, g, wp))
+        cw, _, _ = SA.synth_chip(g, wp)
+        words.append(cw)
+        iwords.append(SA.synth_interactions(g, wp, inter_groups=-(-g // 3)))
+    blob = SA.machine_blob_with_interactions(words, iwords)
+    main_shapes = [(h, 6 * g + (1 if wp else 0)) for h, g, wp in specs]
+    prep_shapes = [(h, 1) for h, g, wp in specs if wp]
+    return dict(names=names, specs=specs, blob=blob, main_shapes=main_shapes, prep_shapes=prep_shapes)

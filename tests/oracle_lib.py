@@ -263,3 +263,27 @@ def gkr_prove_verify(blob, heights, mains, preps, max_log_rows, challenger, gkr_
     if nw < 0:
         raise RuntimeError(f"oracle gkr failed ({nw})")
     return out[:nw].copy()
+
+
+def prove_shard_verify(blob, heights, mains, preps, names, pv, log_stack, max_log_rows, challenger, log_blowup=2, num_queries=124,
+                       pow_bits=16, batch_pow_bits=5, gkr_pow_bits=12):
+    """Whole-shard oracle: returns (prep_commit[8], proof words).  Raises if the restated ShardVerifier rejects."""
+    pd = [np.ascontiguousarray(p, dtype=np.uint32).reshape(-1) for p in preps if p is not None and p.size]
+    md = [np.ascontiguousarray(m, dtype=np.uint32).reshape(-1) for m in mains if m.size]
+    prep_dense = np.concatenate(pd) if pd else np.zeros(1, np.uint32)
+    main_dense = np.concatenate(md) if md else np.zeros(1, np.uint32)
+    H = (C.c_uint64 * len(heights))(*heights)
+    nm = b"".join(n.encode() + b"\0" for n in names)
+    blob = np.ascontiguousarray(blob, dtype=np.uint32)
+    pv = np.ascontiguousarray(pv, dtype=np.uint32)
+    pc = np.zeros(8, np.uint32)
+    cap = 1 << 24
+    out = np.zeros(cap, np.uint32)
+    f = lib().orc_prove_shard_verify
+    f.restype = C.c_int64
+    nw = f(ptr(blob), H, ptr(prep_dense), ptr(main_dense), C.c_char_p(nm), ptr(pv), C.c_uint32(pv.size), C.c_uint32(log_stack),
+           C.c_uint32(max_log_rows), C.c_uint32(log_blowup), C.c_uint32(num_queries), C.c_uint32(pow_bits), C.c_uint32(batch_pow_bits),
+           C.c_uint32(gkr_pow_bits), ptr(challenger.st), ptr(pc), ptr(out), C.c_uint64(cap))
+    if nw < 0:
+        raise RuntimeError(f"oracle prove_shard failed ({nw})")
+    return pc, out[:nw].copy()

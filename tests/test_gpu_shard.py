@@ -1,0 +1,51 @@
+"""GPU parity test of the whole shard proof (A1): sp1b200_prove_shard vs the oracle's prove_shard_with_data restatement
+(which runs the restated ShardVerifier::verify_shard on its own proof).  Every proof word and the final challenger state
+must be identical."""
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+from tests.test_oracle import SHARD_SPECS, _synth_machine_gkr
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(spec, log_stack, mlr, seed, nq=8, pow_bits=4, batch_bits=2, gkr_bits=3):
+    from sp1_b200 import Lib
+    rng = np.random.default_rng(seed)
+    blob, heights, mains, preps, pv = _synth_machine_gkr(rng, spec)
+    names = [f"Chip{i:02d}" for i in range(len(heights))]
+    ch = O.Challenger(); ch.observe(O.rand_field(rng, 9))
+    och = ch.clone()
+    opc, owords = O.prove_shard_verify(blob, heights, mains, preps, names, pv, log_stack, mlr, och, num_queries=nq, pow_bits=pow_bits,
+                                       batch_pow_bits=batch_bits, gkr_pow_bits=gkr_bits)
+    lib = Lib(0, log_stacking_height=log_stack, max_log_row_count=mlr, num_queries=nq, pow_bits=pow_bits, batch_pow_bits=batch_bits,
+              gkr_pow_bits=gkr_bits)
+    mach = lib.machine_create(blob)
+    prep_tabs = [p for p in preps if p is not None]
+    prep_round = None
+    if prep_tabs:
+        pc, prep_round = lib.jagged_commit(prep_tabs)
+        assert (pc == opc).all(), "preprocessed commitment differs"
+    parts = [np.ascontiguousarray(m).reshape(-1) for m in mains if m.size]
+    main_dense = np.ascontiguousarray(np.concatenate(parts))
+    st = ch.st.copy()
+    words = lib.prove_shard(mach, prep_round, main_dense, heights, names, pv, st)
+    assert words.size == owords.size, (words.size, owords.size, words[:6], owords[:6])
+    bad = np.nonzero(words != owords)[0]
+    assert bad.size == 0, f"first differing words {bad[:8]} of {words.size} (sections {owords[:6]})"
+    assert (st == och.st).all()
+    if prep_round is not None:
+        lib.jagged_round_free(prep_round)
+    lib.machine_free(mach)
+    lib.close()
+
+
+@pytest.mark.parametrize("spec,log_stack,mlr", SHARD_SPECS)
+def test_prove_shard_matches_oracle(spec, log_stack, mlr):
+    _run(spec, log_stack, mlr, seed=1200 + mlr)
+
+
+def test_prove_shard_medium():
+    spec = [(4096, 2, True), (1024 + 32, 3, False), (0, 1, False), (8192, 1, True), (2048, 4, False)]
+    _run(spec, 12, 13, seed=99, nq=16, pow_bits=8, batch_bits=5, gkr_bits=6)

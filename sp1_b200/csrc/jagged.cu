@@ -590,10 +590,10 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
     for (uint32_t r = 0; r < n_rounds; r++) handles.push_back(rounds[r]->stacked);
     std::vector<uint32_t> pt(point.size() * 4);
     for (size_t i = 0; i < point.size(); i++) point[i].store(&pt[4 * i]);
-    std::vector<uint32_t> proof(cap ? cap : 1);
+    // the stacked proof is written straight into the caller's buffer; the jagged sections are appended after it
     uint64_t nw = 0;
-    SP1_TRY(sp1b200_stacked_prove(ctx, handles.data(), n_rounds, pt.data(), (uint32_t)point.size(), h_replay, chal, proof.data(), cap, &nw));
-    proof.resize(nw);
+    SP1_TRY(sp1b200_stacked_prove(ctx, handles.data(), n_rounds, pt.data(), (uint32_t)point.size(), h_replay, chal, h_proof, cap, &nw));
+    std::vector<uint32_t> proof;
     auto put = [&](const uint32_t* p, size_t n) { proof.insert(proof.end(), p, p + n); };
     auto put1 = [&](uint32_t v) { proof.push_back(v); };
     // sumcheck proof
@@ -617,9 +617,9 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
     put1(lm);
     t_all.stop();
     memcpy(h_chal, chal, sizeof(chal));
-    if (h_words) *h_words = proof.size();
-    if (proof.size() > cap) return sp1b200_set_error("jagged_prove: proof needs %zu words, capacity %llu", proof.size(), (unsigned long long)cap);
-    if (h_proof) memcpy(h_proof, proof.data(), proof.size() * 4);
+    if (h_words) *h_words = nw + proof.size();
+    if (nw + proof.size() > cap) return sp1b200_set_error("jagged_prove: proof needs %llu words, capacity %llu", (unsigned long long)(nw + proof.size()), (unsigned long long)cap);
+    if (h_proof) memcpy(h_proof + nw, proof.data(), proof.size() * 4);
     return nullptr;
 }
 

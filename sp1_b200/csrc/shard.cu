@@ -8,6 +8,7 @@
 #include "machine.cuh"
 #include "pcs.cuh"
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -76,15 +77,16 @@ sp1b200_err sp1b200_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* m, sp1b
     }
     uint32_t st[34];
     ch.store(st);
+    // uninitialised scratch for the phase outputs (zero-filling 3 x 64 MiB would cost more than some of the phases)
     const uint64_t scratch_cap = (uint64_t)1 << 24;
-    std::vector<uint32_t> gkr(scratch_cap);
+    std::unique_ptr<uint32_t[]> gkr_buf(new uint32_t[scratch_cap]), zc_buf(new uint32_t[scratch_cap]), ev_buf(new uint32_t[scratch_cap]);
+    uint32_t* gkr = gkr_buf.get();
     uint64_t n_gkr = 0;
-    SP1_TRY(sp1b200_logup_gkr(ctx, m, h_heights, d_main.data(), d_prep.data(), h_replay_witnesses, st, gkr.data(), scratch_cap, &n_gkr));
-    gkr.resize(n_gkr);
+    SP1_TRY(sp1b200_logup_gkr(ctx, m, h_heights, d_main.data(), d_prep.data(), h_replay_witnesses, st, gkr, scratch_cap, &n_gkr));
     // tail of the gkr words: point (mlr ext) | per chip {main, prep openings} | witness
     size_t total_w = 0;
     for (auto& c : m->chips) total_w += c.main_w + c.prep_w;
-    const uint32_t* tail = gkr.data() + n_gkr - 1 - 4 * total_w - 4 * mlr;
+    const uint32_t* tail = gkr + n_gkr - 1 - 4 * total_w - 4 * mlr;
     const uint32_t* gkr_point = tail;
     const uint32_t* openings = tail + 4 * mlr;
     ch.load(st);
@@ -100,13 +102,12 @@ sp1b200_err sp1b200_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* m, sp1b
         }
     }
     ch.store(st);
-    std::vector<uint32_t> zc(scratch_cap);
+    uint32_t* zc = zc_buf.get();
     uint64_t n_zc = 0;
-    SP1_TRY(sp1b200_zerocheck(ctx, m, h_heights, d_main.data(), d_prep.data(), h_pv, n_pv, gkr_point, alpha.c, gamma.c, claims.data(), st, zc.data(),
+    SP1_TRY(sp1b200_zerocheck(ctx, m, h_heights, d_main.data(), d_prep.data(), h_pv, n_pv, gkr_point, alpha.c, gamma.c, claims.data(), st, zc,
                               scratch_cap, &n_zc));
-    zc.resize(n_zc);
     // zerocheck words: [mlr] { [5] coeffs(20) } x mlr | claimed_sum 4 | point 4 mlr | eval 4 | per chip {prep evals, main evals}
-    const uint32_t* zpoint = zc.data() + 1 + (size_t)mlr * 21 + 4;
+    const uint32_t* zpoint = zc + 1 + (size_t)mlr * 21 + 4;
     const uint32_t* zopen = zpoint + 4 * mlr + 4;
     std::vector<uint32_t> jclaims;
     {
@@ -122,22 +123,25 @@ sp1b200_err sp1b200_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* m, sp1b
     std::vector<sp1b200_jagged_round*> rounds;
     if (prep_round) rounds.push_back(prep_round);
     rounds.push_back(main_round);
-    std::vector<uint32_t> ev(scratch_cap);
+    uint32_t* ev = ev_buf.get();
     uint64_t n_ev = 0;
     SP1_TRY(sp1b200_jagged_prove(ctx, rounds.data(), (uint32_t)rounds.size(), zpoint, jclaims.data(), h_replay_witnesses ? h_replay_witnesses + 1 : nullptr,
-                                 st, ev.data(), scratch_cap, &n_ev));
-    ev.resize(n_ev);
+                                 st, ev, scratch_cap, &n_ev));
     memcpy(h_chal, st, sizeof(st));
-    std::vector<uint32_t> out{5, 8, (uint32_t)n_gkr, (uint32_t)n_zc, (uint32_t)n_ev, n_pv};
-    out.insert(out.end(), commit, commit + 8);
-    out.insert(out.end(), gkr.begin(), gkr.end());
-    out.insert(out.end(), zc.begin(), zc.end());
-    out.insert(out.end(), ev.begin(), ev.end());
-    out.insert(out.end(), h_pv, h_pv + n_pv);
+    const uint64_t total = 6 + 8 + n_gkr + n_zc + n_ev + n_pv;
     t_all.stop();
-    if (h_words) *h_words = out.size();
-    if (out.size() > cap) return sp1b200_set_error("prove_shard: proof needs %zu words, capacity %llu", out.size(), (unsigned long long)cap);
-    if (h_proof) memcpy(h_proof, out.data(), out.size() * 4);
+    if (h_words) *h_words = total;
+    if (total > cap) return sp1b200_set_error("prove_shard: proof needs %llu words, capacity %llu", (unsigned long long)total, (unsigned long long)cap);
+    if (h_proof) {
+        uint32_t* o = h_proof;
+        const uint32_t hdr[6] = {5, 8, (uint32_t)n_gkr, (uint32_t)n_zc, (uint32_t)n_ev, n_pv};
+        memcpy(o, hdr, 24); o += 6;
+        memcpy(o, commit, 32); o += 8;
+        memcpy(o, gkr, n_gkr * 4); o += n_gkr;
+        memcpy(o, zc, n_zc * 4); o += n_zc;
+        memcpy(o, ev, n_ev * 4); o += n_ev;
+        memcpy(o, h_pv, n_pv * 4);
+    }
     return nullptr;
 }
 }

@@ -155,7 +155,7 @@ class Lib:
         n = len(handles)
         arr = (C.c_void_p * n)(*[h.value for h in handles])
         point = np.ascontiguousarray(point, dtype=np.uint32)
-        proof = np.zeros(cap_words, np.uint32)
+        proof = np.empty(cap_words, np.uint32)
         nwords = C.c_uint64()
         rw = None if replay is None else np.ascontiguousarray(replay, dtype=np.uint32)
         self._chk(self.L.sp1b200_stacked_prove(self.ctx, arr, C.c_uint32(n), _ptr(point), C.c_uint32(point.shape[0]),
@@ -196,7 +196,7 @@ class Lib:
         arr = (C.c_void_p * n)(*[h.value for h in handles])
         z = np.ascontiguousarray(z_row, dtype=np.uint32)
         cl = np.ascontiguousarray(claims, dtype=np.uint32)
-        proof = np.zeros(cap_words, np.uint32)
+        proof = np.empty(cap_words, np.uint32)
         nwords = C.c_uint64()
         rw = None if replay is None else np.ascontiguousarray(replay, dtype=np.uint32)
         self._chk(self.L.sp1b200_jagged_prove(self.ctx, arr, C.c_uint32(n), _ptr(z), _ptr(cl), _ptr(rw),
@@ -220,7 +220,7 @@ class Lib:
         M = (C.c_void_p * n)(*[t.data_ptr() if t is not None and t.numel() else None for t in d_mains])
         Pp = (C.c_void_p * n)(*[t.data_ptr() if t is not None and t.numel() else None for t in d_preps])
         pv = np.ascontiguousarray(pv, dtype=np.uint32)
-        out = np.zeros(cap_words, np.uint32)
+        out = np.empty(cap_words, np.uint32)
         nw = C.c_uint64()
         self._chk(self.L.sp1b200_zerocheck(self.ctx, machine, H, M, Pp, _ptr(pv), C.c_uint32(pv.size),
                                            _ptr(np.ascontiguousarray(gkr_point, dtype=np.uint32)),
@@ -235,7 +235,7 @@ class Lib:
         H = (C.c_uint64 * n)(*heights)
         M = (C.c_void_p * n)(*[t.data_ptr() if t is not None and t.numel() else None for t in d_mains])
         Pp = (C.c_void_p * n)(*[t.data_ptr() if t is not None and t.numel() else None for t in d_preps])
-        out = np.zeros(cap_words, np.uint32)
+        out = np.empty(cap_words, np.uint32)
         nw = C.c_uint64()
         rw = None if replay is None else np.ascontiguousarray([replay], dtype=np.uint32)
         self._chk(self.L.sp1b200_logup_gkr(self.ctx, machine, H, M, Pp, _ptr(rw), _ptr(challenger_state), _ptr(out),
@@ -247,7 +247,7 @@ class Lib:
         H = (C.c_uint64 * n)(*heights)
         NM = (C.c_char_p * n)(*[s.encode() for s in names])
         pv = np.ascontiguousarray(pv, dtype=np.uint32)
-        out = np.zeros(cap_words, np.uint32)
+        out = np.empty(cap_words, np.uint32)
         nw = C.c_uint64()
         rw = None if replay is None else np.ascontiguousarray(replay, dtype=np.uint32)
         self._chk(self.L.sp1b200_prove_shard(self.ctx, machine, prep_round, _ptr(main_dense), H, NM, _ptr(pv), C.c_uint32(pv.size),

@@ -158,7 +158,10 @@ def main():
     stream = torch.cuda.ExternalStream(lib.stream(), device=dev)
 
     from sp1_b200 import synth_air as SA
-    mach = W.synthetic_machine(args.workload, seed=42 + rank)
+    from sp1_b200 import shards as SH
+    # one shard per rank per step (weak scaling): rank r proves shard r of a world-sized batch of independent shards
+    my_shard = SH.shards_of_rank(world, rank, world)[0]
+    mach = W.synthetic_machine(args.workload, seed=42)
     specs, names = mach["specs"], mach["names"]
     heights = [h for h, _, _ in specs]
     cells = W.area_of(mach["main_shapes"])
@@ -167,7 +170,7 @@ def main():
     pv = ((np.array([pv0, 5, 6, 7], dtype=np.uint64) << np.uint64(32)) % np.uint64(W.P)).astype(np.uint32)
     mains, preps = [], []
     for i, (h, g, wp) in enumerate(specs):
-        m_, p_ = SA.synth_trace_cuda(h, g, wp, pv0, 1000 * (rank + 1) + i, dev)
+        m_, p_ = SA.synth_trace_cuda(h, g, wp, pv0, SH.shard_seed(0, my_shard) + i, dev)
         mains.append(m_)
         if wp:
             preps.append(p_)
@@ -216,11 +219,7 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = SH.max_over_ranks(e0.elapsed_time(e1), dev)
         return ms, lib.launch_count() - l0, nbytes
 
     for _ in range(args.warmup):

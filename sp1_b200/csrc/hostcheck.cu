@@ -2,6 +2,9 @@
 // test-suite check the exact code the kernels run (lazy-reduction bounds, half-product Montgomery forms) against the
 // oracle before any GPU time is spent.  Test support only; not part of include/sp1b200.h.
 #include "poseidon2.cuh"
+#include "hostfield.hpp"
+#include "zc_lower.hpp"
+#include <cstring>
 
 extern "C" {
 void sp1b200_hostcheck_permute(uint32_t* states, uint64_t n) {
@@ -28,5 +31,63 @@ void sp1b200_hostcheck_ext_inv(const uint32_t* a, uint32_t* out, uint64_t n) {
 }
 void sp1b200_hostcheck_field(const uint32_t* a, const uint32_t* b, uint32_t* add, uint32_t* sub, uint32_t* mul, uint64_t n) {
     for (uint64_t i = 0; i < n; i++) { add[i] = kb::add(a[i], b[i]); sub[i] = kb::sub(a[i], b[i]); mul[i] = kb::mul(a[i], b[i]); }
+}
+
+// Evaluate ONE chip's constraint program on one row (base-field values) two ways: the bytecode as given, and the stream
+// produced by zc_lower (what the zerocheck kernels interpret).  chip = the per-chip words of the machine blob
+// (sp1b200_machine_create).  out[0..4) = sum_k alpha_pows[assert_alphas[k]] * value_k (original), out[4..8) = lowered;
+// returns the lowered register pressure, or -1 on a lowering error.
+int sp1b200_hostcheck_zc_lower(const uint32_t* chip, const uint32_t* main_row, const uint32_t* prep_row, const uint32_t* pv,
+                               const uint32_t* alpha_pows, uint32_t window, uint32_t* out, uint32_t* n_lowered) {
+    using hf::E4;
+    const uint32_t* b = chip;
+    HostProg hp;
+    b += 3;  // main_w prep_w n_constraints
+    const uint32_t n_regs = *b++;
+    const uint32_t ni = *b++, nl = *b++, nc = *b++, np = *b++, na = *b++;
+    hp.instrs.resize(ni); memcpy(hp.instrs.data(), b, ni * 8); b += 2 * ni;
+    hp.leaves.resize(nl); memcpy(hp.leaves.data(), b, nl * 8); b += 2 * nl;
+    hp.consts.assign(b, b + nc); b += nc;
+    hp.publics.assign(b, b + np); b += np;
+    hp.assert_regs.assign(b, b + na); b += na;
+    hp.assert_alphas.assign(b, b + na); b += na;
+    auto leaf = [&](const LeafRef& l) { return l.source == LEAF_MAIN ? main_row[l.col] : prep_row[l.col]; };
+    {
+        std::vector<uint32_t> regs(n_regs ? n_regs : 1, 0);
+        for (const DagInstr& in : hp.instrs) {
+            switch (in.opcode) {
+                case BC_LOAD_LEAF: regs[in.out] = leaf(hp.leaves[in.a]); break;
+                case BC_LOAD_CONST: regs[in.out] = hp.consts[in.a]; break;
+                case BC_LOAD_PUBLIC: regs[in.out] = pv[hp.publics[in.a]]; break;
+                case BC_ADD_F: regs[in.out] = hf::add(regs[in.a], regs[in.b]); break;
+                case BC_SUB_F: regs[in.out] = hf::sub(regs[in.a], regs[in.b]); break;
+                case BC_MUL_F: regs[in.out] = hf::mul(regs[in.a], regs[in.b]); break;
+                case BC_NEG_F: regs[in.out] = hf::neg(regs[in.a]); break;
+            }
+        }
+        E4 acc;
+        for (size_t k = 0; k < hp.assert_regs.size(); k++) acc = acc + E4::load(alpha_pows + 4 * hp.assert_alphas[k]) * regs[hp.assert_regs[k]];
+        acc.store(out);
+    }
+    ZcLowered L = zc_lower(hp, window);
+    if (!L.error.empty()) return -1;
+    if (n_lowered) *n_lowered = (uint32_t)L.instrs.size();
+    std::vector<uint32_t> rf(L.n_regs, 0);
+    E4 acc;
+    for (const ZcInstr& in : L.instrs) {
+        switch (in.op) {
+            case ZC_LOAD_MAIN: rf[in.out] = main_row[(uint32_t)in.a | ((uint32_t)in.b << 16)]; break;
+            case ZC_LOAD_PREP: rf[in.out] = prep_row[(uint32_t)in.a | ((uint32_t)in.b << 16)]; break;
+            case ZC_CONST: rf[in.out] = hp.consts[in.a]; break;
+            case ZC_PUBLIC: rf[in.out] = pv[hp.publics[in.a]]; break;
+            case ZC_ADD: { uint32_t x = rf[in.a], y = rf[in.b]; rf[in.out] = hf::add(x, y); break; }
+            case ZC_SUB: { uint32_t x = rf[in.a], y = rf[in.b]; rf[in.out] = hf::sub(x, y); break; }
+            case ZC_MUL: { uint32_t x = rf[in.a], y = rf[in.b]; rf[in.out] = hf::mul(x, y); break; }
+            case ZC_NEG: rf[in.out] = hf::neg(rf[in.a]); break;
+            case ZC_ASSERT: acc = acc + E4::load(alpha_pows + 4 * in.b) * rf[in.a]; break;
+        }
+    }
+    acc.store(out + 4);
+    return (int)L.n_regs;
 }
 }

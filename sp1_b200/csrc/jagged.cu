@@ -288,6 +288,151 @@ __global__ void __launch_bounds__(128) bp_round_kernel(const uint8_t* __restrict
     if (threadIdx.x < 8) partial[blockIdx.x * 8 + threadIdx.x] = red[threadIdx.x & 3][threadIdx.x >> 2];
 }
 
+// ---- prefix / suffix form of the same evaluation -----------------------------------------------------------------
+// The evaluation is  e0^T M_0 M_1 ... M_hl init  with one 4x4 transfer matrix per layer, M_l = M(cur_l, next_l).  In sumcheck
+// round r only ONE layer holds the free variable: layers above it still see the column's boolean prefix-sum bits (and, in
+// the second half, next-coordinates that were bound earlier and never change again), layers below it see coordinates that
+// were bound in earlier rounds.  So per column k:  value = P_k . M_layer(lambda) . T_k[layer + 1]  with
+//   T_k[l] = M_l ... M_hl init   (suffix table, one pass per half: bp_suffix_kernel)
+//   P_k    = e0^T M_0 ... M_{layer-1}   (prefix row vector, one vector-matrix product per round: bp_update_kernel)
+// i.e. two small products per (column, node) and round instead of hl+1 (the reference keeps the same prefix/suffix states,
+// sp1-gpu/crates/sys/lib/jagged_assist).  Every product is exact field arithmetic, so the round polynomials are unchanged.
+struct BpMat { Ext ri[4], cc[4]; };
+__device__ __forceinline__ void bp_layer_coeffs(const uint32_t* __restrict__ ri_eq, uint32_t layer, uint32_t hl, const Ext& cur, const Ext& nxt, BpMat& m) {
+    if (layer < hl) {
+        const uint32_t* e = ri_eq + (size_t)layer * 16;
+        m.ri[0] = kb::ext_load(e); m.ri[1] = kb::ext_load(e + 4); m.ri[2] = kb::ext_load(e + 8); m.ri[3] = kb::ext_load(e + 12);
+    } else { m.ri[0] = kb::ext_one(); m.ri[1] = m.ri[2] = m.ri[3] = kb::ext_zero(); }
+    const Ext cn = kb::ext_mul(cur, nxt);
+    m.cc[3] = cn; m.cc[2] = kb::ext_sub(cur, cn); m.cc[1] = kb::ext_sub(nxt, cn);
+    m.cc[0] = kb::ext_sub(kb::ext_sub(kb::ext_one(), cur), m.cc[1]);
+}
+// out = M res   (column form; same accumulation order as bp_round_kernel)
+__device__ __forceinline__ void bp_apply(const BpMat& m, const Ext res[4], Ext out[4]) {
+#pragma unroll
+    for (int st = 0; st < 4; st++) {
+        Ext acc = kb::ext_zero();
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            Ext inner = kb::ext_zero();
+            bool any = false;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int o = bp_transition(a >> 1, a & 1, c >> 1, c & 1, st);
+                if (o >= 0) { inner = kb::ext_add(inner, kb::ext_mul(m.cc[c], res[o])); any = true; }
+            }
+            if (any) acc = kb::ext_add(acc, kb::ext_mul(m.ri[a], inner));
+        }
+        out[st] = acc;
+    }
+}
+// out = P M   (row form)
+__device__ __forceinline__ void bp_apply_row(const BpMat& m, const Ext P[4], Ext out[4]) {
+    Ext o4[4] = {kb::ext_zero(), kb::ext_zero(), kb::ext_zero(), kb::ext_zero()};
+#pragma unroll
+    for (int st = 0; st < 4; st++)
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const Ext q = kb::ext_mul(P[st], m.ri[a]);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int o = bp_transition(a >> 1, a & 1, c >> 1, c & 1, st);
+                if (o >= 0) o4[o] = kb::ext_add(o4[o], kb::ext_mul(q, m.cc[c]));
+            }
+        }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = o4[i];
+}
+__device__ __forceinline__ Ext bp_bit(const uint8_t* b, uint32_t pos) { return b[pos] ? kb::ext_one() : kb::ext_zero(); }
+
+// T[(l * nk + k) * 4 + s], l = hl+1 .. 0.  second_half: next-coordinates are the bound values rho_by_pos[dim-1-l]
+__global__ void __launch_bounds__(128) bp_suffix_kernel(const uint8_t* __restrict__ bits, uint32_t nk, uint32_t dim, int second_half,
+                                                        const uint32_t* __restrict__ rho_by_pos, const uint32_t* __restrict__ ri_eq,
+                                                        uint32_t* __restrict__ T) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nk) return;
+    const uint32_t hl = dim / 2;
+    const uint8_t* b = bits + (size_t)k * dim;
+    Ext res[4] = {kb::ext_zero(), kb::ext_zero(), kb::ext_one(), kb::ext_zero()};
+    for (int s = 0; s < 4; s++) kb::ext_store(T + (((size_t)(hl + 1) * nk + k) * 4 + s) * 4, res[s]);
+    for (int layer = (int)hl; layer >= 0; layer--) {
+        Ext cur = kb::ext_zero(), nxt = kb::ext_zero();
+        if ((uint32_t)layer < hl) {
+            cur = bp_bit(b, hl - 1 - layer);
+            nxt = second_half ? kb::ext_load(rho_by_pos + 4 * (dim - 1 - layer)) : bp_bit(b, dim - 1 - layer);
+        }
+        BpMat m;
+        bp_layer_coeffs(ri_eq, (uint32_t)layer, hl, cur, nxt, m);
+        Ext nres[4];
+        bp_apply(m, res, nres);
+        for (int s = 0; s < 4; s++) { res[s] = nres[s]; kb::ext_store(T + (((size_t)layer * nk + k) * 4 + s) * 4, res[s]); }
+    }
+}
+// round r: thread (k, node) -> zc[k] * inter[k] * eq(lambda, bit) * P_k . M_layer(lambda_node) . T_k[layer+1]
+__global__ void __launch_bounds__(128) bp_round2_kernel(const uint8_t* __restrict__ bits, uint32_t nk, uint32_t dim, uint32_t round,
+                                                        const uint32_t* __restrict__ rho_by_pos, const uint32_t* __restrict__ ri_eq,
+                                                        const uint32_t* __restrict__ zc, const uint32_t* __restrict__ inter,
+                                                        const uint32_t* __restrict__ P, const uint32_t* __restrict__ T, Ext half,
+                                                        uint32_t* __restrict__ partial) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    Ext v = kb::ext_zero();
+    const uint32_t k = t >> 1, node = t & 1;
+    const uint32_t hl = dim / 2, split = dim - round - 1;
+    if (k < nk) {
+        const uint8_t* b = bits + (size_t)k * dim;
+        const bool second = round >= hl;
+        const uint32_t layer = second ? round - hl : round;
+        const Ext lam = node ? half : kb::ext_zero();
+        const Ext cur = second ? lam : bp_bit(b, hl - 1 - layer);
+        const Ext nxt = second ? kb::ext_load(rho_by_pos + 4 * (dim - 1 - layer)) : lam;
+        BpMat m;
+        bp_layer_coeffs(ri_eq, layer, hl, cur, nxt, m);
+        Ext res[4], w[4];
+        for (int s = 0; s < 4; s++) res[s] = kb::ext_load(T + (((size_t)(layer + 1) * nk + k) * 4 + s) * 4);
+        bp_apply(m, res, w);
+        Ext val = kb::ext_zero();
+        if (round == 0 || round == hl) val = w[0];  // P_k = e0^T at the start of either half (bp_update_kernel resets it after this round)
+        else
+            for (int s = 0; s < 4; s++) val = kb::ext_add(val, kb::ext_mul(kb::ext_load(P + ((size_t)k * 4 + s) * 4), w[s]));
+        const Ext eqv = node ? half : (b[split] ? kb::ext_zero() : kb::ext_one());
+        v = kb::ext_mul(kb::ext_mul(kb::ext_load(zc + 4 * k), val), kb::ext_mul(kb::ext_load(inter + 4 * k), eqv));
+    }
+    __shared__ uint32_t red[4][128];
+    for (int l = 0; l < 4; l++) red[l][threadIdx.x] = v.c[l];
+    __syncthreads();
+    for (int s = 64; s >= 2; s >>= 1) {  // keep parity (node) separate: stop at 2
+        if ((int)threadIdx.x < s)
+            for (int l = 0; l < 4; l++) red[l][threadIdx.x] = kb::add(red[l][threadIdx.x], red[l][threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x < 8) partial[blockIdx.x * 8 + threadIdx.x] = red[threadIdx.x & 3][threadIdx.x >> 2];
+}
+// after round r's challenge: bind position split = dim-1-r: rho_by_pos, inter[k] *= eq(alpha, bit), P_k <- P_k M_layer(bound)
+// (at the switch to the second half P_k restarts at e0^T: the caller rebuilds T with the bound next-coordinates first)
+__global__ void __launch_bounds__(128) bp_update_kernel(const uint8_t* __restrict__ bits, uint32_t nk, uint32_t dim, uint32_t round, Ext alpha,
+                                                        uint32_t* __restrict__ rho_by_pos, const uint32_t* __restrict__ ri_eq,
+                                                        uint32_t* __restrict__ inter, uint32_t* __restrict__ P) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t hl = dim / 2, split = dim - round - 1;
+    if (k == 0) kb::ext_store(rho_by_pos + 4 * split, alpha);
+    if (k >= nk) return;
+    const uint8_t* b = bits + (size_t)k * dim;
+    const Ext f = b[split] ? alpha : kb::ext_sub(kb::ext_one(), alpha);
+    kb::ext_store(inter + 4 * k, kb::ext_mul(kb::ext_load(inter + 4 * k), f));
+    const bool second = round >= hl;
+    const uint32_t layer = second ? round - hl : round;
+    Ext Pk[4], out[4];
+    for (int s = 0; s < 4; s++) Pk[s] = kb::ext_load(P + ((size_t)k * 4 + s) * 4);
+    if (round == hl) { Pk[0] = kb::ext_one(); Pk[1] = Pk[2] = Pk[3] = kb::ext_zero(); }
+    const Ext cur = second ? alpha : bp_bit(b, hl - 1 - layer);
+    // second half: the next-coordinate of this layer was bound in round `layer` (written before this kernel ran)
+    const Ext nxt = second ? kb::ext_load(rho_by_pos + 4 * (dim - 1 - layer)) : alpha;
+    BpMat m;
+    bp_layer_coeffs(ri_eq, layer, hl, cur, nxt, m);
+    bp_apply_row(m, Pk, out);
+    for (int s = 0; s < 4; s++) kb::ext_store(P + ((size_t)k * 4 + s) * 4, out[s]);
+}
+
 // inter[k] *= alpha * x + (1 - alpha) * (1 - x),  x = bits[k][dim - 1 - round]
 __global__ void bp_fix_kernel(const uint8_t* __restrict__ bits, uint32_t nk, uint32_t dim, uint32_t round, Ext alpha, uint32_t* __restrict__ inter) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -561,9 +706,21 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
         ch.observe_n(je_claimed.c, 4);
         E4 cl = je_claimed;
         je_words.push_back(dim);
+        // prefix / suffix states (see bp_suffix_kernel): T for the first half now, rebuilt once when the second half starts
+        uint32_t *d_T, *d_P, *d_rho_pos;
+        SP1_TRY(mem.alloc((void**)&d_T, (size_t)(hl + 2) * nk * 64));
+        SP1_TRY(mem.alloc((void**)&d_P, (size_t)nk * 64));
+        SP1_TRY(mem.alloc((void**)&d_rho_pos, (size_t)dim * 16));
+        {
+            std::vector<E4> p0((size_t)nk * 4);
+            for (uint32_t k = 0; k < nk; k++) p0[4 * k] = E4::one();
+            SP1_CUDA(cudaMemcpyAsync(d_P, p0.data(), p0.size() * 16, cudaMemcpyHostToDevice, st));
+            SP1_CUDA(cudaMemsetAsync(d_rho_pos, 0, (size_t)dim * 16, st));
+        }
+        SP1_LAUNCH(ctx, bp_suffix_kernel, blocks_for(nk, 128), 128, 0, d_bits, nk, dim, 0, d_rho_pos, d_ri, d_T);
         for (uint32_t round = 0; round < dim; round++) {
-            if (round) SP1_CUDA(cudaMemcpyAsync(d_rhos, rhos.data(), rhos.size() * 16, cudaMemcpyHostToDevice, st));
-            SP1_LAUNCH(ctx, bp_round_kernel, nblk, 128, 0, d_bits, nk, dim, dim - round - 1, 1, d_rhos, d_ri, d_zc, d_inter, dhalf, d_part);
+            if (round == hl) SP1_LAUNCH(ctx, bp_suffix_kernel, blocks_for(nk, 128), 128, 0, d_bits, nk, dim, 1, d_rho_pos, d_ri, d_T);
+            SP1_LAUNCH(ctx, bp_round2_kernel, nblk, 128, 0, d_bits, nk, dim, round, d_rho_pos, d_ri, d_zc, d_inter, d_P, d_T, dhalf, d_part);
             E4 y0, yh;
             SP1_TRY(sum_partials(ctx, d_part, nblk, y0, yh));
             E4 y1 = cl - y0;
@@ -576,7 +733,7 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
             rhos.insert(rhos.begin(), alpha);
             cl = eval3(c, alpha);
             Ext da{{alpha.c[0], alpha.c[1], alpha.c[2], alpha.c[3]}};
-            SP1_LAUNCH(ctx, bp_fix_kernel, blocks_for(nk, 128), 128, 0, d_bits, nk, dim, round, da, d_inter);
+            SP1_LAUNCH(ctx, bp_update_kernel, blocks_for(nk, 128), 128, 0, d_bits, nk, dim, round, da, d_rho_pos, d_ri, d_inter, d_P);
         }
         je_eval = cl;
         t.stop();

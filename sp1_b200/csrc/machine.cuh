@@ -10,10 +10,12 @@ static_assert(sizeof(DagInstr) == 8 && sizeof(LeafRef) == 8, "bytecode layout mu
 enum : uint8_t { BC_LOAD_LEAF = 0, BC_LOAD_CONST = 1, BC_LOAD_PUBLIC = 2, BC_ADD_F = 3, BC_SUB_F = 4, BC_MUL_F = 5, BC_NEG_F = 6 };
 enum : uint8_t { LEAF_PREP = 2, LEAF_MAIN = 4 };
 
+struct ZcInstr;    // lowered instruction stream (zc_lower.hpp)
 struct ChipProg {  // device pointers into the machine arena
     const DagInstr* instrs; const LeafRef* leaves; const uint32_t* consts; const uint32_t* publics;
     const uint32_t* assert_regs; const uint32_t* assert_alphas;
     uint32_t n_instrs, n_asserts, n_regs, main_w, prep_w, n_constraints;
+    const ZcInstr* zc; uint32_t n_zc, zc_regs;  // re-scheduled program interpreted by the zerocheck kernels
 };
 struct HostProg {  // host copy for the padded-row adjustment (one evaluation on the all-zero row per proof)
     std::vector<DagInstr> instrs; std::vector<LeafRef> leaves; std::vector<uint32_t> consts, publics, assert_regs, assert_alphas;
@@ -23,6 +25,8 @@ struct sp1b200_machine {
     std::vector<ChipProg> chips;
     std::vector<HostProg> host;
     uint32_t* d_arena = nullptr;
+    void* d_zc_arena = nullptr;     // all chips' lowered programs
+    ChipProg* d_chips = nullptr;    // device copy of `chips`
     void* interactions = nullptr;  // HostInteractions (gkr.cu)
 };
 

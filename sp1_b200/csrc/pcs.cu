@@ -72,10 +72,10 @@ __global__ void __launch_bounds__(256) batch_columns_kernel(const uint32_t* __re
     for (; c + 2 <= ncols; c += 2) {
         uint32_t x = __ldg(p + c * h), y = __ldg(p + (c + 1) * h);
         const uint32_t* k0 = scoef + 4 * c;
-        a0 = kb::add(a0, kb::monty_reduce((uint64_t)x * k0[0] + (uint64_t)y * k0[4]));
-        a1 = kb::add(a1, kb::monty_reduce((uint64_t)x * k0[1] + (uint64_t)y * k0[5]));
-        a2 = kb::add(a2, kb::monty_reduce((uint64_t)x * k0[2] + (uint64_t)y * k0[6]));
-        a3 = kb::add(a3, kb::monty_reduce((uint64_t)x * k0[3] + (uint64_t)y * k0[7]));
+        a0 = kb::add(a0, kb::monty_reduce2((uint64_t)x * k0[0] + (uint64_t)y * k0[4]));
+        a1 = kb::add(a1, kb::monty_reduce2((uint64_t)x * k0[1] + (uint64_t)y * k0[5]));
+        a2 = kb::add(a2, kb::monty_reduce2((uint64_t)x * k0[2] + (uint64_t)y * k0[6]));
+        a3 = kb::add(a3, kb::monty_reduce2((uint64_t)x * k0[3] + (uint64_t)y * k0[7]));
     }
     if (c < ncols) {
         uint32_t x = __ldg(p + c * h);

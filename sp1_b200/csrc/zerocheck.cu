@@ -4,9 +4,12 @@
 // GPU twin it replaces: sp1-gpu/crates/zerocheck/src/prover.rs + sys/lib/zerocheck/{sequential,gkr_sweep,geq_corrections,pad_adj}.cu.
 // Input contract for the constraints = the reference GPU prover's bytecode (sys/include/zerocheck/sequential.cuh:13-49):
 // DagInstr / LeafRef / BcOp, asserts as (register, alpha index) pairs.
-// HOW: one launch per (chip, round) with the three evaluation nodes {0,2,4} on grid.z (as the reference does), the
-// eq table built once and halved per round, trace columns kept column-major (base field in round 0, EF afterwards),
-// geq / padded-row corrections and the 5-node interpolation done on the host from three EF partial sums per chip.
+// HOW (B200): every chip's bytecode is re-scheduled at upload (zc_lower.hpp) so that its live set fits a SHARED-MEMORY
+// register file; one launch per round covers ALL chips (block -> (chip, row chunk), evaluation node on grid.y), a second tiny
+// launch reduces the per-block partial sums, and one 5 KB copy + one sync per round feeds the host transcript.  The linear
+// opening-batching term  sum_j gamma^j col_j  is evaluated once per row pair (at 0 and 1) instead of at every node.
+// The eq table is built once and halved per round; trace columns stay column-major (base field in round 0, EF afterwards);
+// geq / padded-row corrections and the 5-node interpolation run on the host from nine EF partial sums per chip.
 #include "ctx.cuh"
 #include "challenger.cuh"
 #include "hostfield.hpp"
@@ -16,11 +19,15 @@
 #include <vector>
 
 #include "machine.cuh"
+#include "zc_lower.hpp"
 
 namespace {
 
 using kb::Ext;
 using hf::E4;
+
+constexpr int ZC_BLOCK = 128;
+constexpr int ZC_LOCAL_REGS = 256;  // fallback tier: register file in local memory
 
 template <class K> struct Ops;
 template <> struct Ops<uint32_t> {
@@ -55,72 +62,158 @@ __device__ __forceinline__ K interp_pair(const K* __restrict__ base, uint32_t co
     return node == 1 ? O::add(z, d2) : O::add(z, O::add(d2, d2));
 }
 
-// partial[(blockIdx.x * 3 + node) * 4 ..] = Σ_{rows of the block} E[i] * ( [constraints](node) + Σ_j gkr_pow_j col_j(node) )
-template <class K, int MAXR>
-__global__ void __launch_bounds__(128) zc_sum_kernel(ChipProg prog, const K* __restrict__ main, const K* __restrict__ prep, uint64_t h,
-                                                     const uint32_t* __restrict__ pv, const uint32_t* __restrict__ alpha_pows,
-                                                     const uint32_t* __restrict__ gkr_pows, const uint32_t* __restrict__ E, int skip_node0_constraints,
-                                                     uint32_t* __restrict__ partial) {
-    using O = Ops<K>;
-    const int node = blockIdx.z;  // 0,1,2 <-> t = 0,2,4
-    const uint64_t terms = (h + 1) / 2;
-    K regs[MAXR];
-    Ext acc = kb::ext_zero();
-    const bool run_constraints = !(skip_node0_constraints && node == 0);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < terms; i += (uint64_t)gridDim.x * blockDim.x) {
-        Ext row = kb::ext_zero();
-        if (run_constraints) {
-            for (uint32_t pc = 0; pc < prog.n_instrs; pc++) {
-                const DagInstr in = prog.instrs[pc];
-                switch (in.opcode) {
-                    case BC_LOAD_LEAF: {
-                        const LeafRef l = prog.leaves[in.a];
-                        regs[in.out] = interp_pair<K>(l.source == LEAF_MAIN ? main : prep, l.col, h, i, node);
-                        break;
-                    }
-                    case BC_LOAD_CONST: regs[in.out] = O::from_base(prog.consts[in.a]); break;
-                    case BC_LOAD_PUBLIC: regs[in.out] = O::from_base(pv[prog.publics[in.a]]); break;
-                    case BC_ADD_F: regs[in.out] = O::add(regs[in.a], regs[in.b]); break;
-                    case BC_SUB_F: regs[in.out] = O::sub(regs[in.a], regs[in.b]); break;
-                    case BC_MUL_F: regs[in.out] = O::mul(regs[in.a], regs[in.b]); break;
-                    case BC_NEG_F: regs[in.out] = O::sub(O::zero(), regs[in.a]); break;
-                    default: __trap();
-                }
-            }
-            for (uint32_t k = 0; k < prog.n_asserts; k++)
-                row = kb::ext_add(row, O::scale(kb::ext_load(alpha_pows + 4 * prog.assert_alphas[k]), regs[prog.assert_regs[k]]));
-        }
-        for (uint32_t j = 0; j < prog.main_w; j++)
-            row = kb::ext_add(row, O::scale(kb::ext_load(gkr_pows + 4 * j), interp_pair<K>(main, j, h, i, node)));
-        for (uint32_t j = 0; j < prog.prep_w; j++)
-            row = kb::ext_add(row, O::scale(kb::ext_load(gkr_pows + 4 * (prog.main_w + j)), interp_pair<K>(prep, j, h, i, node)));
-        acc = kb::ext_add(acc, kb::ext_mul(row, kb::ext_load(E + 4 * i)));
+// one chip in one round
+struct ZcJob {
+    const void* main; const void* prep; const uint32_t* alpha_pows; uint64_t h;
+    uint32_t blk_start, nblk, chip, pad;
+};
+struct ZcFixJob {
+    const void* main; const void* prep; uint32_t* out; uint64_t h;
+    uint32_t main_w, prep_w, blk_start, pad;
+};
+
+template <class J>
+__device__ __forceinline__ int find_job(const J* __restrict__ jobs, int n, uint32_t blk) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].blk_start <= blk) lo = mid; else hi = mid - 1;
     }
-    __shared__ uint32_t red[4][128];
-    for (int l = 0; l < 4; l++) red[l][threadIdx.x] = acc.c[l];
-    __syncthreads();
-    for (int s = 64; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s)
-            for (int l = 0; l < 4; l++) red[l][threadIdx.x] = kb::add(red[l][threadIdx.x], red[l][threadIdx.x + s]);
-        __syncthreads();
-    }
-    if (threadIdx.x < 4) partial[(blockIdx.x * 3 + node) * 4 + threadIdx.x] = red[threadIdx.x][0];
+    return lo;
 }
 
-// out[j][i] = in[j][2i] + alpha (in[j][2i+1] - in[j][2i]),  i < ceil(h/2)   (column-major, EF out)
-template <class K>
-__global__ void zc_fix_kernel(const K* __restrict__ in, uint64_t h, uint32_t w, Ext alpha, uint32_t* __restrict__ out) {
+// register file: shared memory [reg][thread] (SMEM) or a local array (fallback for programs whose pressure does not fit)
+template <class K, bool SMEM> struct RegFile;
+template <class K> struct RegFile<K, true> {
+    K* base;
+    __device__ __forceinline__ RegFile(unsigned char* smem) : base(reinterpret_cast<K*>(smem) + threadIdx.x) {}
+    __device__ __forceinline__ K get(uint32_t r) const { return base[r * ZC_BLOCK]; }
+    __device__ __forceinline__ void set(uint32_t r, const K& v) { base[r * ZC_BLOCK] = v; }
+};
+template <class K> struct RegFile<K, false> {
+    K regs[ZC_LOCAL_REGS];
+    __device__ __forceinline__ RegFile(unsigned char*) {}
+    __device__ __forceinline__ K get(uint32_t r) const { return regs[r]; }
+    __device__ __forceinline__ void set(uint32_t r, const K& v) { regs[r] = v; }
+};
+
+// partial[(blockIdx.x * 3 + node) * 3 + {0,1,2}] =
+//   0: sum_rows E[i] * [constraints](node)     1 (node 0 only): sum_rows E[i] * sum_j g_j col_j(0)     2 (node 0 only): same at 1
+template <class K, bool SMEM>
+__global__ void __launch_bounds__(ZC_BLOCK) zc_sum_kernel(const ZcJob* __restrict__ jobs, int n_jobs, const ChipProg* __restrict__ chips,
+                                                          const uint32_t* __restrict__ pv, const uint32_t* __restrict__ gkr_pows,
+                                                          const uint32_t* __restrict__ E, int first_round, uint32_t* __restrict__ partial) {
     using O = Ops<K>;
-    const uint64_t nh = (h + 1) / 2;
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nh * w) return;
-    uint64_t j = t / nh, i = t - j * nh;
-    K a = O::load(in + j * h, 2 * i);
-    K b = (2 * i + 1 < h) ? O::load(in + j * h, 2 * i + 1) : O::zero();
+    extern __shared__ __align__(16) unsigned char zc_smem[];
+    __shared__ uint32_t red[3][4][ZC_BLOCK / 32];
+    const ZcJob job = jobs[find_job(jobs, n_jobs, blockIdx.x)];
+    const ChipProg& prog = chips[job.chip];
+    const K* main = static_cast<const K*>(job.main);
+    const K* prep = static_cast<const K*>(job.prep);
+    const uint64_t h = job.h;
+    const int node = blockIdx.y;  // 0,1,2 <-> t = 0,2,4
+    const uint64_t terms = (h + 1) / 2;
+    RegFile<K, SMEM> rf(zc_smem);
+    Ext acc_c = kb::ext_zero(), acc_a = kb::ext_zero(), acc_b = kb::ext_zero();
+    const bool run_constraints = !(first_round && node == 0);
+    const ZcInstr* __restrict__ zc = prog.zc;
+    const uint32_t n_zc = prog.n_zc;
+    for (uint64_t i = (uint64_t)(blockIdx.x - job.blk_start) * ZC_BLOCK + threadIdx.x; i < terms; i += (uint64_t)job.nblk * ZC_BLOCK) {
+        const Ext e = kb::ext_load(E + 4 * i);
+        if (run_constraints) {
+            Ext row = kb::ext_zero();
+            ZcInstr in = n_zc ? zc[0] : ZcInstr{};
+            for (uint32_t pc = 0; pc < n_zc; pc++) {
+                const ZcInstr nxt = zc[pc + 1 < n_zc ? pc + 1 : pc];  // prefetch: the stream is block-uniform and L1 resident
+                switch (in.op) {
+                    case ZC_LOAD_MAIN: rf.set(in.out, interp_pair<K>(main, (uint32_t)in.a | ((uint32_t)in.b << 16), h, i, node)); break;
+                    case ZC_LOAD_PREP: rf.set(in.out, interp_pair<K>(prep, (uint32_t)in.a | ((uint32_t)in.b << 16), h, i, node)); break;
+                    case ZC_CONST: rf.set(in.out, O::from_base(prog.consts[in.a])); break;
+                    case ZC_PUBLIC: rf.set(in.out, O::from_base(pv[prog.publics[in.a]])); break;
+                    case ZC_ADD: { const K x = rf.get(in.a), y = rf.get(in.b); rf.set(in.out, O::add(x, y)); break; }
+                    case ZC_SUB: { const K x = rf.get(in.a), y = rf.get(in.b); rf.set(in.out, O::sub(x, y)); break; }
+                    case ZC_MUL: { const K x = rf.get(in.a), y = rf.get(in.b); rf.set(in.out, O::mul(x, y)); break; }
+                    case ZC_NEG: { const K x = rf.get(in.a); rf.set(in.out, O::sub(O::zero(), x)); break; }
+                    case ZC_ASSERT: row = kb::ext_add(row, O::scale(kb::ext_load(job.alpha_pows + 4 * in.b), rf.get(in.a))); break;
+                    default: __trap();
+                }
+                in = nxt;
+            }
+            acc_c = kb::ext_add(acc_c, kb::ext_mul(row, e));
+        }
+        if (node == 0) {
+            // the opening-batching term is linear in the row variable: evaluate it at 0 and 1 only
+            Ext s0 = kb::ext_zero(), s1 = kb::ext_zero();
+            const bool has_o = 2 * i + 1 < h;
+            for (uint32_t j = 0; j < prog.main_w; j++) {
+                const Ext g = kb::ext_load(gkr_pows + 4 * j);
+                const K* c = main + (uint64_t)j * h;
+                s0 = kb::ext_add(s0, O::scale(g, O::load(c, 2 * i)));
+                if (has_o) s1 = kb::ext_add(s1, O::scale(g, O::load(c, 2 * i + 1)));
+            }
+            for (uint32_t j = 0; j < prog.prep_w; j++) {
+                const Ext g = kb::ext_load(gkr_pows + 4 * (prog.main_w + j));
+                const K* c = prep + (uint64_t)j * h;
+                s0 = kb::ext_add(s0, O::scale(g, O::load(c, 2 * i)));
+                if (has_o) s1 = kb::ext_add(s1, O::scale(g, O::load(c, 2 * i + 1)));
+            }
+            acc_a = kb::ext_add(acc_a, kb::ext_mul(s0, e));
+            acc_b = kb::ext_add(acc_b, kb::ext_mul(s1, e));
+        }
+    }
+    // block reduction: warp shuffles, then one warp over the per-warp sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Ext* accs[3] = {&acc_c, &acc_a, &acc_b};
+    const int n_acc = node == 0 ? 3 : 1;
+    for (int a = 0; a < n_acc; a++)
+        for (int l = 0; l < 4; l++) {
+            uint32_t v = accs[a]->c[l];
+            for (int s = 16; s > 0; s >>= 1) v = kb::add(v, __shfl_down_sync(0xffffffffu, v, s));
+            if (lane == 0) red[a][l][warp] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const int a = threadIdx.x >> 2, l = threadIdx.x & 3;
+        uint32_t v = 0;
+        if (a < n_acc)
+            for (int w = 0; w < ZC_BLOCK / 32; w++) v = kb::add(v, red[a][l][w]);
+        partial[((uint64_t)(blockIdx.x * 3 + node) * 3 + a) * 4 + l] = v;
+    }
+}
+
+// out[(job * 3 + node) * 3 + slot] = sum over the job's blocks
+__global__ void __launch_bounds__(128) zc_reduce_kernel(const ZcJob* __restrict__ jobs, const uint32_t* __restrict__ partial, uint32_t* __restrict__ out) {
+    const ZcJob job = jobs[blockIdx.x];
+    __shared__ uint32_t red[36][4];
+    const int slot = threadIdx.x >> 2, part = threadIdx.x & 3;  // 32 groups of 4 threads; 36 words = 9 ext -> loop
+    for (int w = slot; w < 36; w += 32) {
+        uint32_t v = 0;
+        for (uint32_t b = part; b < job.nblk; b += 4) v = kb::add(v, partial[(uint64_t)(job.blk_start + b) * 36 + w]);
+        red[w][part] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 36) {
+        const uint32_t* r = red[threadIdx.x];
+        out[blockIdx.x * 36 + threadIdx.x] = kb::add(kb::add(r[0], r[1]), kb::add(r[2], r[3]));
+    }
+}
+
+// out[j][i] = in[j][2i] + alpha (in[j][2i+1] - in[j][2i]),  i < ceil(h/2)   (column-major, EF out; main columns then preprocessed)
+template <class K>
+__global__ void __launch_bounds__(256) zc_fix_kernel(const ZcFixJob* __restrict__ jobs, int n_jobs, Ext alpha) {
+    using O = Ops<K>;
+    const ZcFixJob job = jobs[find_job(jobs, n_jobs, blockIdx.x)];
+    const uint64_t h = job.h, nh = (h + 1) / 2;
+    const uint64_t t = (uint64_t)(blockIdx.x - job.blk_start) * 256 + threadIdx.x;
+    if (t >= nh * (job.main_w + job.prep_w)) return;
+    const uint64_t j = t / nh, i = t - j * nh;
+    const K* in = j < job.main_w ? static_cast<const K*>(job.main) + j * h : static_cast<const K*>(job.prep) + (j - job.main_w) * h;
+    K a = O::load(in, 2 * i);
+    K b = (2 * i + 1 < h) ? O::load(in, 2 * i + 1) : O::zero();
     Ext r;
     if constexpr (sizeof(K) == 4) r = kb::ext_add(kb::ext_from_base(a), kb::ext_mul_base(alpha, kb::sub(b, a)));
     else r = kb::ext_add(a, kb::ext_mul(alpha, kb::ext_sub(b, a)));
-    kb::ext_store(out + 4 * (j * nh + i), r);
+    kb::ext_store(job.out + 4 * t, r);
 }
 
 __global__ void zc_eq_table_kernel(const uint32_t* __restrict__ point, int k, uint32_t* __restrict__ E) {
@@ -197,20 +290,6 @@ struct DevFree {
 };
 inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
-template <class K>
-sp1b200_err launch_sum(sp1b200_ctx* ctx, const ChipProg& p, const void* main, const void* prep, uint64_t h, const uint32_t* d_pv, const uint32_t* d_ap,
-                       const uint32_t* d_gp, const uint32_t* d_E, int first, uint32_t* d_partial, unsigned nblk) {
-    dim3 g(nblk, 1, 3);
-    auto go = [&](auto kern) -> sp1b200_err {
-        SP1_LAUNCH(ctx, kern, g, 128, 0, p, (const K*)main, (const K*)prep, h, d_pv, d_ap, d_gp, d_E, first, d_partial);
-        return nullptr;
-    };
-    if (p.n_regs <= 64) return go(zc_sum_kernel<K, 64>);
-    if (p.n_regs <= 256) return go(zc_sum_kernel<K, 256>);
-    if (p.n_regs <= 1024) return go(zc_sum_kernel<K, 1024>);
-    return sp1b200_set_error("zerocheck: chip needs %u registers (> 1024)", p.n_regs);
-}
-
 }  // namespace
 
 extern "C" {
@@ -244,6 +323,22 @@ sp1b200_err sp1b200_machine_create(sp1b200_ctx* ctx, const uint32_t* h_blob, uin
         m->chips.push_back(p); m->host.push_back(std::move(hp));
     }
     m->interactions = sp1b200_parse_interactions(b, end, n);
+    // re-schedule every chip's program for the shared-memory register file (zc_lower.hpp) and upload the streams
+    std::vector<ZcInstr> all;
+    std::vector<size_t> zc_off(n);
+    for (uint32_t c = 0; c < n; c++) {
+        ZcLowered L = zc_lower(m->host[c]);
+        if (!L.error.empty()) return sp1b200_set_error("machine_create: chip %u: %s", c, L.error.c_str());
+        zc_off[c] = all.size();
+        m->chips[c].n_zc = (uint32_t)L.instrs.size();
+        m->chips[c].zc_regs = L.n_regs;
+        all.insert(all.end(), L.instrs.begin(), L.instrs.end());
+    }
+    SP1_CUDA(cudaMalloc(&m->d_zc_arena, all.size() * sizeof(ZcInstr) + 16));
+    if (!all.empty()) SP1_CUDA(cudaMemcpyAsync(m->d_zc_arena, all.data(), all.size() * sizeof(ZcInstr), cudaMemcpyHostToDevice, ctx->stream));
+    for (uint32_t c = 0; c < n; c++) m->chips[c].zc = static_cast<const ZcInstr*>(m->d_zc_arena) + zc_off[c];
+    SP1_CUDA(cudaMalloc((void**)&m->d_chips, (n ? n : 1) * sizeof(ChipProg)));
+    if (n) SP1_CUDA(cudaMemcpyAsync(m->d_chips, m->chips.data(), n * sizeof(ChipProg), cudaMemcpyHostToDevice, ctx->stream));
     SP1_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = m.release();
     return nullptr;
@@ -252,8 +347,12 @@ void sp1b200_machine_free(sp1b200_ctx*, sp1b200_machine* m) {
     if (!m) return;
     sp1b200_free_interactions(m->interactions);
     cudaFree(m->d_arena);
+    cudaFree(m->d_zc_arena);
+    cudaFree(m->d_chips);
     delete m;
 }
+// peak register pressure of a chip's re-scheduled program (tests / diagnostics)
+uint32_t sp1b200_machine_chip_regs(const sp1b200_machine* m, uint32_t chip) { return chip < m->chips.size() ? m->chips[chip].zc_regs : 0; }
 uint32_t sp1b200_machine_num_chips(const sp1b200_machine* m) { return (uint32_t)m->chips.size(); }
 
 // ShardProver::zerocheck (crates/hypercube/src/prover/shard.rs:474-646).
@@ -275,55 +374,142 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     const E4 alpha = E4::load(h_alpha), gamma = E4::load(h_gamma);
 
     struct St {
-        uint64_t h; void *main, *prep; bool ext = false;
+        uint64_t h;
         std::vector<E4> zeta; E4 eq_adj = E4::one(), pra; VGeq vg;
-        uint32_t *d_ap, *d_gp; uint32_t *buf[2] = {nullptr, nullptr}; // EF ping-pong (main+prep columns back to back)
     };
     std::vector<St> S(nchips);
-    size_t maxc = 0, maxw = 0;
-    for (auto& c : m->chips) { maxc = std::max<size_t>(maxc, c.n_constraints); maxw = std::max<size_t>(maxw, c.main_w + c.prep_w); }
+    size_t maxc = 0, maxw = 0, total_w = 0, total_c = 0;
+    for (auto& c : m->chips) {
+        maxc = std::max<size_t>(maxc, c.n_constraints); maxw = std::max<size_t>(maxw, c.main_w + c.prep_w);
+        total_w += c.main_w + c.prep_w; total_c += c.n_constraints ? c.n_constraints : 1;
+    }
     std::vector<E4> pw(maxc ? maxc : 1); pw[0] = E4::one();
     for (size_t i = 1; i < pw.size(); i++) pw[i] = pw[i - 1] * alpha;
     std::vector<E4> gw(maxw ? maxw : 1); gw[0] = gamma;
     for (size_t i = 1; i < gw.size(); i++) gw[i] = gw[i - 1] * gamma;
-    uint32_t *d_pv, *d_gw;
+    uint32_t *d_pv, *d_gw, *d_ap;
     SP1_TRY(mem.alloc((void**)&d_pv, (n_pv ? n_pv : 1) * 4));
     if (n_pv) SP1_CUDA(cudaMemcpyAsync(d_pv, h_pv, n_pv * 4, cudaMemcpyHostToDevice, st));
     SP1_TRY(mem.alloc((void**)&d_gw, gw.size() * 16));
     SP1_CUDA(cudaMemcpyAsync(d_gw, gw.data(), gw.size() * 16, cudaMemcpyHostToDevice, st));
     std::vector<E4> gp(mlr);
     for (uint32_t i = 0; i < mlr; i++) gp[i] = E4::load(h_gkr_point + 4 * i);
-    uint64_t max_terms = 1;
+    // per chip: reversed alpha powers (one upload), state, regions of the two EF ping-pong arenas, slot in the final-values buffer
+    std::vector<E4> all_ap; all_ap.reserve(total_c);
+    std::vector<size_t> ap_off(nchips), woff(nchips);
+    std::vector<uint64_t> boff0(nchips), boff1(nchips);
+    uint64_t b0 = 0, b1 = 0; size_t wsum = 0;
     for (size_t k = 0; k < nchips; k++) {
         const ChipProg& p = m->chips[k];
         St& s = S[k];
         s.h = h_heights[k];
         if (s.h > ((uint64_t)1 << mlr)) return sp1b200_set_error("zerocheck: chip %zu height exceeds 2^%u", k, mlr);
-        s.main = (void*)d_main[k]; s.prep = p.prep_w ? (void*)d_prep[k] : nullptr;
+        if (p.zc_regs > ZC_LOCAL_REGS) return sp1b200_set_error("zerocheck: chip %zu needs %u live registers (> %d)", k, p.zc_regs, ZC_LOCAL_REGS);
         s.zeta = gp;
         std::vector<E4> rev(pw.begin(), pw.begin() + p.n_constraints);
         std::reverse(rev.begin(), rev.end());
-        SP1_TRY(mem.alloc((void**)&s.d_ap, (rev.size() ? rev.size() : 1) * 16));
-        if (!rev.empty()) SP1_CUDA(cudaMemcpyAsync(s.d_ap, rev.data(), rev.size() * 16, cudaMemcpyHostToDevice, st));
-        s.d_gp = d_gw;
+        ap_off[k] = all_ap.size();
+        all_ap.insert(all_ap.end(), rev.begin(), rev.end());
+        if (rev.empty()) all_ap.push_back(E4());
         s.pra = host_eval_zero_row(m->host[k], h_pv, rev, p.n_regs);
         s.vg.threshold = (uint32_t)s.h; s.vg.geq_c = E4::one();
         const uint64_t nh = (s.h + 1) / 2;
-        max_terms = std::max(max_terms, nh);
         const size_t w = p.main_w + p.prep_w;
-        SP1_TRY(mem.alloc((void**)&s.buf[0], (size_t)w * nh * 16));
-        SP1_TRY(mem.alloc((void**)&s.buf[1], (size_t)w * ((nh + 1) / 2) * 16));
+        boff0[k] = b0; b0 += (uint64_t)w * nh * 4;
+        boff1[k] = b1; b1 += (uint64_t)w * ((nh + 1) / 2) * 4;
+        woff[k] = wsum; wsum += w;
     }
+    SP1_TRY(mem.alloc((void**)&d_ap, all_ap.size() * 16));
+    SP1_CUDA(cudaMemcpyAsync(d_ap, all_ap.data(), all_ap.size() * 16, cudaMemcpyHostToDevice, st));
+    uint32_t *d_buf[2], *d_final;
+    SP1_TRY(mem.alloc((void**)&d_buf[0], b0 * 4 + 16));
+    SP1_TRY(mem.alloc((void**)&d_buf[1], b1 * 4 + 16));
+    SP1_TRY(mem.alloc((void**)&d_final, (wsum ? wsum : 1) * 16));
     // eq table over the first mlr-1 coordinates of the gkr point, halved every round
-    uint32_t *d_point, *d_E[2], *d_partial;
+    uint32_t *d_point, *d_E[2];
     SP1_TRY(mem.alloc((void**)&d_point, mlr * 16));
     SP1_CUDA(cudaMemcpyAsync(d_point, h_gkr_point, mlr * 16, cudaMemcpyHostToDevice, st));
     SP1_TRY(mem.alloc((void**)&d_E[0], ((size_t)16 << (mlr - 1))));
     SP1_TRY(mem.alloc((void**)&d_E[1], ((size_t)16 << (mlr > 1 ? mlr - 2 : 0))));
-    const unsigned MAXB = 148 * 4;
-    SP1_TRY(mem.alloc((void**)&d_partial, (size_t)nchips * MAXB * 3 * 16));
     SP1_LAUNCH(ctx, zc_eq_table_kernel, blocks_for((uint64_t)1 << (mlr - 1)), 256, 0, d_point, (int)mlr - 1, d_E[0]);
     int ecur = 0;
+
+    // ---- the whole launch plan is known up front (heights halve deterministically): job tables of every round, one upload ----
+    // tiers of the shared-memory register file (registers per thread); chips above the last tier use the local-memory kernel
+    static const uint32_t TIER_REGS[3] = {16, 48, 96};
+    auto tier_of = [&](uint32_t regs) { for (int t = 0; t < 3; t++) if (regs <= TIER_REGS[t]) return t; return 3; };
+    struct Launch { size_t job0; uint32_t n_jobs, blocks, regs; int tier; };
+    struct RoundPlan { std::vector<Launch> sums; size_t fix0; uint32_t fix_jobs, fix_blocks; std::vector<uint32_t> chip_of_job; size_t job0; };
+    std::vector<RoundPlan> plan(mlr);
+    std::vector<ZcJob> jobs;
+    std::vector<ZcFixJob> fjobs;
+    const unsigned MAXB = 148 * 4;
+    uint32_t max_blocks = 1, max_jobs = 1;
+    {
+        std::vector<uint64_t> hcur(nchips);
+        for (size_t k = 0; k < nchips; k++) hcur[k] = S[k].h;
+        for (uint32_t rd = 0; rd < mlr; rd++) {
+            RoundPlan& R = plan[rd];
+            R.job0 = jobs.size();
+            auto in_main = [&](size_t k) -> const void* {
+                if (rd == 0) return d_main[k];
+                return (rd & 1 ? d_buf[0] + boff0[k] : d_buf[1] + boff1[k]);
+            };
+            auto in_prep = [&](size_t k) -> const void* {
+                const ChipProg& p = m->chips[k];
+                if (!p.prep_w) return nullptr;
+                if (rd == 0) return d_prep[k];
+                return static_cast<const uint32_t*>(in_main(k)) + (uint64_t)p.main_w * hcur[k] * 4;
+            };
+            uint32_t blocks_round = 0;
+            for (int tier = 0; tier < 4; tier++) {
+                Launch Lc{jobs.size(), 0, 0, 0, tier};
+                for (size_t k = 0; k < nchips; k++) {
+                    const ChipProg& p = m->chips[k];
+                    if (!hcur[k] || tier_of(p.zc_regs) != tier) continue;
+                    unsigned nb = blocks_for((hcur[k] + 1) / 2, ZC_BLOCK);
+                    if (nb > MAXB) nb = MAXB;
+                    ZcJob j{in_main(k), in_prep(k), d_ap + 4 * ap_off[k], hcur[k], Lc.blocks, nb, (uint32_t)k, 0};
+                    jobs.push_back(j);
+                    R.chip_of_job.push_back((uint32_t)k);
+                    Lc.n_jobs++; Lc.blocks += nb; Lc.regs = std::max(Lc.regs, p.zc_regs);
+                }
+                if (Lc.n_jobs) { R.sums.push_back(Lc); blocks_round += Lc.blocks; }
+            }
+            max_blocks = std::max(max_blocks, blocks_round);
+            max_jobs = std::max<uint32_t>(max_jobs, (uint32_t)R.chip_of_job.size());
+            R.fix0 = fjobs.size(); R.fix_jobs = 0; R.fix_blocks = 0;
+            for (size_t k = 0; k < nchips; k++) {
+                const ChipProg& p = m->chips[k];
+                if (!hcur[k]) continue;
+                const uint64_t nh = (hcur[k] + 1) / 2;
+                uint32_t* out = rd + 1 == mlr ? d_final + 4 * woff[k] : (rd & 1 ? d_buf[1] + boff1[k] : d_buf[0] + boff0[k]);
+                ZcFixJob f{in_main(k), in_prep(k), out, hcur[k], p.main_w, p.prep_w, R.fix_blocks, 0};
+                fjobs.push_back(f);
+                R.fix_jobs++; R.fix_blocks += blocks_for(nh * (p.main_w + p.prep_w), 256);
+                hcur[k] = nh;
+            }
+        }
+    }
+    ZcJob* d_jobs; ZcFixJob* d_fjobs; uint32_t *d_partial, *d_sums;
+    SP1_TRY(mem.alloc((void**)&d_jobs, (jobs.size() + 1) * sizeof(ZcJob)));
+    SP1_TRY(mem.alloc((void**)&d_fjobs, (fjobs.size() + 1) * sizeof(ZcFixJob)));
+    if (!jobs.empty()) SP1_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(ZcJob), cudaMemcpyHostToDevice, st));
+    if (!fjobs.empty()) SP1_CUDA(cudaMemcpyAsync(d_fjobs, fjobs.data(), fjobs.size() * sizeof(ZcFixJob), cudaMemcpyHostToDevice, st));
+    SP1_TRY(mem.alloc((void**)&d_partial, (size_t)max_blocks * 36 * 4));
+    SP1_TRY(mem.alloc((void**)&d_sums, (size_t)max_jobs * 36 * 4));
+    SP1_CUDA(cudaMemsetAsync(d_final, 0, (wsum ? wsum : 1) * 16, st));
+    auto launch_sum = [&](const Launch& Lc, bool ext, int first, uint32_t* part) -> sp1b200_err {
+        dim3 g(Lc.blocks, 3, 1);
+        auto go = [&](auto kern, size_t smem) -> sp1b200_err {
+            if (smem > 48 * 1024) SP1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SP1_LAUNCH(ctx, kern, g, ZC_BLOCK, smem, d_jobs + Lc.job0, (int)Lc.n_jobs, m->d_chips, d_pv, d_gw, d_E[ecur], first, part);
+            return nullptr;
+        };
+        if (Lc.tier == 3) return ext ? go(zc_sum_kernel<Ext, false>, 0) : go(zc_sum_kernel<uint32_t, false>, 0);
+        const size_t regs = Lc.regs;  // the file is sized by the launch's worst chip
+        return ext ? go(zc_sum_kernel<Ext, true>, regs * ZC_BLOCK * 16) : go(zc_sum_kernel<uint32_t, true>, regs * ZC_BLOCK * 4);
+    };
 
     E4 lambda; ch.sample_ext(lambda.c);
     std::vector<E4> round_claims(nchips);
@@ -333,46 +519,46 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     words.push_back(mlr);
     std::vector<E4> point;
     std::vector<std::vector<E4>> unis(nchips);
-    std::vector<unsigned> nblk(nchips);
-    std::vector<uint32_t> hp((size_t)nchips * MAXB * 12);
-    const E4 two = E4::from_base(hf::to_monty(2)), four = E4::from_base(hf::to_monty(4));
+    std::vector<uint32_t> hs((size_t)max_jobs * 36);
+    std::vector<int32_t> job_of_chip(nchips);
+    const E4 two = E4::from_base(hf::to_monty(2)), four = E4::from_base(hf::to_monty(4)), three = E4::from_base(hf::to_monty(3));
     for (uint32_t rd = 0; rd < mlr; rd++) {
-        // launch every chip's three partial sums, then one copy back
-        for (size_t k = 0; k < nchips; k++) {
-            St& s = S[k];
-            nblk[k] = 0;
-            if (s.h == 0) continue;
-            const uint64_t terms = (s.h + 1) / 2;
-            unsigned nb = blocks_for(terms, 128);
-            if (nb > MAXB) nb = MAXB;
-            nblk[k] = nb;
-            const ChipProg& p = m->chips[k];
-            uint32_t* part = d_partial + (size_t)k * MAXB * 12;
-            if (!s.ext) SP1_TRY(launch_sum<uint32_t>(ctx, p, s.main, s.prep, s.h, d_pv, s.d_ap, s.d_gp, d_E[ecur], 1, part, nb));
-            else SP1_TRY(launch_sum<Ext>(ctx, p, s.main, s.prep, s.h, d_pv, s.d_ap, s.d_gp, d_E[ecur], 0, part, nb));
+        const RoundPlan& R = plan[rd];
+        // every chip's partial sums: one launch per register-file tier, one reduction each, one copy back
+        {
+            uint32_t blk = 0; size_t jb = 0;
+            for (const Launch& Lc : R.sums) {
+                SP1_TRY(launch_sum(Lc, rd > 0, rd == 0, d_partial + (size_t)blk * 36));
+                SP1_LAUNCH(ctx, zc_reduce_kernel, Lc.n_jobs, 128, 0, d_jobs + Lc.job0, d_partial + (size_t)blk * 36, d_sums + jb * 36);
+                blk += Lc.blocks; jb += Lc.n_jobs;
+            }
+            if (jb) {
+                SP1_CUDA(cudaMemcpyAsync(hs.data(), d_sums, jb * 36 * 4, cudaMemcpyDeviceToHost, st));
+                SP1_CUDA(cudaStreamSynchronize(st));
+            }
         }
-        SP1_CUDA(cudaMemcpyAsync(hp.data(), d_partial, hp.size() * 4, cudaMemcpyDeviceToHost, st));
-        SP1_CUDA(cudaStreamSynchronize(st));
-        // E[threshold_half] for the geq correction: read the few entries needed
+        std::fill(job_of_chip.begin(), job_of_chip.end(), -1);
+        for (size_t j = 0; j < R.chip_of_job.size(); j++) job_of_chip[R.chip_of_job[j]] = (int32_t)j;
         std::vector<E4> rlc(1);
         for (size_t k = 0; k < nchips; k++) {
             St& s = S[k];
             std::vector<E4>& u = unis[k];
             if (s.h == 0) { u.assign(5, E4()); }
             else {
-                E4 y0, y2, y4;
-                for (unsigned bI = 0; bI < nblk[k]; bI++) {
-                    const uint32_t* q = &hp[((size_t)k * MAXB + bI) * 12];
-                    y0 = y0 + E4::load(q); y2 = y2 + E4::load(q + 4); y4 = y4 + E4::load(q + 8);
-                }
+                // sums: [node][slot] ; y_t = C_t + A + t (B - A) with A, B the opening-batching term at 0 and 1
+                const uint32_t* q = &hs[(size_t)job_of_chip[k] * 36];
+                const E4 A = E4::load(q + 4), B = E4::load(q + 8);
+                E4 y0 = E4::load(q) + A;
+                E4 y2 = E4::load(q + 12) + (B + B) - A;
+                E4 y4 = E4::load(q + 24) + B * four - A * three;
                 const uint64_t th = (s.h + 1) / 2 - 1;
                 const uint64_t esize = (uint64_t)1 << (s.zeta.size() - 1);
+                // E[th] = eq(bits of th, zeta[0 .. len-1)) (most significant bit first): 21 host products instead of a device read + sync
                 E4 eth;
                 if (th < esize) {
-                    uint32_t w4[4];
-                    SP1_CUDA(cudaMemcpyAsync(w4, d_E[ecur] + 4 * th, 16, cudaMemcpyDeviceToHost, st));
-                    SP1_CUDA(cudaStreamSynchronize(st));
-                    eth = E4::load(w4);
+                    const size_t kk = s.zeta.size() - 1;
+                    eth = E4::one();
+                    for (size_t t = 0; t < kk; t++) eth = eth * (((th >> (kk - 1 - t)) & 1) ? s.zeta[t] : E4::one() - s.zeta[t]);
                 }
                 const E4 last = s.zeta.back();
                 const E4 msb = s.eq_adj * eth;
@@ -397,28 +583,19 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
         E4 a; ch.sample_ext(a.c);
         point.insert(point.begin(), a);
         const Ext da{{a.c[0], a.c[1], a.c[2], a.c[3]}};
+        if (R.fix_jobs) {
+            if (rd == 0) SP1_LAUNCH(ctx, zc_fix_kernel<uint32_t>, R.fix_blocks, 256, 0, d_fjobs + R.fix0, (int)R.fix_jobs, da);
+            else SP1_LAUNCH(ctx, zc_fix_kernel<Ext>, R.fix_blocks, 256, 0, d_fjobs + R.fix0, (int)R.fix_jobs, da);
+        }
         for (size_t k = 0; k < nchips; k++) {
             St& s = S[k];
-            const ChipProg& p = m->chips[k];
             round_claims[k] = host_eval_poly(unis[k], a);
             s.vg = s.vg.fix_last(a);
             if (s.h == 0) continue;
-            const uint64_t nh = (s.h + 1) / 2;
-            uint32_t* outb = s.buf[rd & 1];
-            uint32_t* out_main = outb;
-            uint32_t* out_prep = outb + (size_t)p.main_w * nh * 4;
-            if (!s.ext) {
-                SP1_LAUNCH(ctx, zc_fix_kernel<uint32_t>, blocks_for(nh * p.main_w), 256, 0, (const uint32_t*)s.main, s.h, p.main_w, da, out_main);
-                if (p.prep_w) SP1_LAUNCH(ctx, zc_fix_kernel<uint32_t>, blocks_for(nh * p.prep_w), 256, 0, (const uint32_t*)s.prep, s.h, p.prep_w, da, out_prep);
-            } else {
-                SP1_LAUNCH(ctx, zc_fix_kernel<Ext>, blocks_for(nh * p.main_w), 256, 0, (const Ext*)s.main, s.h, p.main_w, da, out_main);
-                if (p.prep_w) SP1_LAUNCH(ctx, zc_fix_kernel<Ext>, blocks_for(nh * p.prep_w), 256, 0, (const Ext*)s.prep, s.h, p.prep_w, da, out_prep);
-            }
-            s.main = out_main; s.prep = p.prep_w ? out_prep : nullptr; s.ext = true;
             const E4 last = s.zeta.back();
             s.eq_adj = s.eq_adj * (a * last + (E4::one() - a) * (E4::one() - last));
             s.zeta.pop_back();
-            s.h = nh;
+            s.h = (s.h + 1) / 2;
         }
         if (rd + 1 < mlr) {
             const uint64_t n_out = (uint64_t)1 << (mlr - 2 - rd);
@@ -431,21 +608,20 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     words.insert(words.end(), claimed_sum.c, claimed_sum.c + 4);
     for (auto& x : point) words.insert(words.end(), x.c, x.c + 4);
     words.insert(words.end(), final_eval.c, final_eval.c + 4);
-    // opened values: one EF row per chip (prep then main); observe as the reference does
+    // opened values: one EF row per chip (main columns then preprocessed, zeros for absent chips), fetched with one copy;
+    // observed and emitted prep-first as the reference does
+    std::vector<uint32_t> fin((wsum ? wsum : 1) * 4);
+    SP1_CUDA(cudaMemcpyAsync(fin.data(), d_final, fin.size() * 4, cudaMemcpyDeviceToHost, st));
+    SP1_CUDA(cudaStreamSynchronize(st));
     ch.observe(hf::to_monty(nchips));
     for (size_t k = 0; k < nchips; k++) {
         const ChipProg& p = m->chips[k];
-        St& s = S[k];
-        std::vector<uint32_t> mv((size_t)p.main_w * 4, 0), pvv((size_t)p.prep_w * 4, 0);
-        if (s.h) {
-            SP1_CUDA(cudaMemcpyAsync(mv.data(), s.main, mv.size() * 4, cudaMemcpyDeviceToHost, st));
-            if (p.prep_w) SP1_CUDA(cudaMemcpyAsync(pvv.data(), s.prep, pvv.size() * 4, cudaMemcpyDeviceToHost, st));
-            SP1_CUDA(cudaStreamSynchronize(st));
-        }
-        ch.observe(hf::to_monty(p.prep_w)); ch.observe_n(pvv.data(), pvv.size());
-        ch.observe(hf::to_monty(p.main_w)); ch.observe_n(mv.data(), mv.size());
-        words.insert(words.end(), pvv.begin(), pvv.end());
-        words.insert(words.end(), mv.begin(), mv.end());
+        const uint32_t* mv = &fin[4 * woff[k]];
+        const uint32_t* pvv = mv + 4 * (size_t)p.main_w;
+        ch.observe(hf::to_monty(p.prep_w)); ch.observe_n(pvv, (size_t)p.prep_w * 4);
+        ch.observe(hf::to_monty(p.main_w)); ch.observe_n(mv, (size_t)p.main_w * 4);
+        words.insert(words.end(), pvv, pvv + (size_t)p.prep_w * 4);
+        words.insert(words.end(), mv, mv + (size_t)p.main_w * 4);
     }
     t_all.stop();
     ch.store(h_chal);

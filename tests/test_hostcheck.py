@@ -59,3 +59,58 @@ def test_device_field_and_ext_sources_on_host():
         assert (out[i] == e).all()
         L.orc_ext_inv(O.ptr(x[i]), O.ptr(e))
         assert (inv[i] == e).all()
+
+
+def _check_lowering(chip_words, main_w, prep_w, n_constraints, seed, window=24):
+    rng = np.random.default_rng(seed)
+    cw = np.array(chip_words, dtype=np.uint32)
+    out = np.zeros(8, np.uint32)
+    nl = C.c_uint32(0)
+    regs = None
+    for _ in range(6):
+        main_row = O.rand_field(rng, max(main_w, 1))
+        prep_row = O.rand_field(rng, max(prep_w, 1))
+        pv = O.rand_field(rng, 8)
+        ap = O.rand_field(rng, (max(n_constraints, 1), 4))
+        regs = _L().sp1b200_hostcheck_zc_lower(cw.ctypes.data_as(O.u32p), main_row.ctypes.data_as(O.u32p), prep_row.ctypes.data_as(O.u32p),
+                                               pv.ctypes.data_as(O.u32p), ap.ctypes.data_as(O.u32p), C.c_uint32(window),
+                                               out.ctypes.data_as(O.u32p), C.byref(nl))
+        assert regs > 0
+        assert (out[:4] == out[4:]).all()
+        assert out[:4].any()          # random rows do not satisfy the constraints: a non-trivial comparison
+    return regs, nl.value
+
+
+def test_constraint_lowering_preserves_the_row_polynomial():
+    """zc_lower (re-scheduling for the shared-memory register file) vs the bytecode as given, same row, same alpha powers"""
+    from sp1_b200 import synth_air as SA
+    for groups, wp in [(1, False), (3, True), (7, False), (41, True)]:
+        words, main_w, prep_w = SA.synth_chip(groups, wp)
+        n_constraints = words[2]
+        for window in (0, 4, 24, 10_000):
+            regs, _ = _check_lowering(words, main_w, prep_w, n_constraints, seed=groups + window, window=window)
+            # SSA input: one register per instruction; lowered: a handful regardless of the chip's size
+            assert regs <= 16, (groups, wp, window, regs)
+
+
+def test_constraint_lowering_handles_register_reuse_dead_code_and_leaf_asserts():
+    from sp1_b200 import synth_air as SA
+    a = SA.Asm()
+    x = a.leaf(SA.LEAF_MAIN, 0)
+    y = a.leaf(SA.LEAF_MAIN, 1)
+    k = a.const(5)
+    t = a.op(SA.MUL, x, y)
+    dead = a.op(SA.ADD, t, k)                       # never asserted
+    u = a.op(SA.SUB, t, k)
+    a.assert_zero(u)
+    a.assert_zero(x)                                # assert directly on a leaf
+    v = a.op(SA.NEG, u)
+    a.assert_zero(v)
+    a.assert_zero(u)                                # the same value under a second alpha power
+    # overwrite a register in place (non-SSA): reg[t] = reg[t] * reg[y]; assert it
+    a.instrs.append((SA.MUL, t, t, y))
+    a.assert_zero(t)
+    words = a.words(2, 0)
+    regs, n_low = _check_lowering(words, 2, 0, words[2], seed=99, window=2)
+    assert regs <= 4
+    assert dead >= 0

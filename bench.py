@@ -187,7 +187,7 @@ def main():
     chal0 = HostChallenger().st.copy()
     padded_cells = ((cells + (1 << 21) - 1) >> 21) << 21
 
-    phase_names = ["commit.rs_encode", "commit.merkle", "shard.commit", "gkr.circuit", "gkr.rounds", "gkr.openings", "gkr.total",
+    phase_names = ["commit.rs_encode", "commit.merkle", "shard.commit", "gkr.circuit", "gkr.rounds", "gkr.openings", "gkr.total", "gkr.host_wait", "gkr.host_interaction", "gkr.host_transcript",
                    "zerocheck.total", "jagged.little_poly", "jagged.sumcheck", "jagged.eval_sumcheck", "open.batch", "open.fri_rounds",
                    "open.queries", "open.total", "jagged.total", "shard.total"]
     acc = {}

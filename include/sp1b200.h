@@ -45,7 +45,7 @@ typedef struct sp1b200_params {
 #define SP1B200_CHALLENGER_WORDS 34
 #define SP1B200_DIGEST_WORDS 8
 
-/* ---- context / runtime (replaces sp1-gpu/crates/cuda TaskScope + sys/lib/runtime/*.cu) ---------------- */
+/* ---- context / runtime (replaces sp1-gpu/crates/cuda TaskScope + sys/lib/runtime/{all}.cu) ---------------- */
 sp1b200_err sp1b200_ctx_create(int device, const sp1b200_params* params, sp1b200_ctx** out);
 void sp1b200_ctx_destroy(sp1b200_ctx* ctx);
 sp1b200_err sp1b200_ctx_sync(sp1b200_ctx* ctx);
@@ -64,7 +64,7 @@ uint64_t sp1b200_launch_count(sp1b200_ctx* ctx);
  * measured with CUDA events on the context stream; -1 if unknown */
 float sp1b200_last_phase_ms(sp1b200_ctx* ctx, const char* phase);
 
-/* ---- kernel-level entry points (replace the per-kernel FFI of sp1-gpu/crates/sys/src/*.rs) ------------- */
+/* ---- kernel-level entry points (replace the per-kernel FFI of sp1-gpu/crates/sys/src/{all}.rs) ------------- */
 
 /* Poseidon2 permutation of n independent 16-word states (poseidon2.cuh:46-80). */
 sp1b200_err sp1b200_poseidon2_permute(sp1b200_ctx* ctx, uint32_t* states_any, uint64_t n);
@@ -156,7 +156,7 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
                                  uint32_t* h_challenger34, uint32_t* h_proof, uint64_t proof_cap_words,
                                  uint64_t* h_proof_words);
 
-/* ---- zerocheck (replaces sp1-gpu/crates/zerocheck + sys/lib/zerocheck/*.cu) ------------------------------------ */
+/* ---- zerocheck (replaces sp1-gpu/crates/zerocheck + sys/lib/zerocheck/{all}.cu) ------------------------------------ */
 
 typedef struct sp1b200_machine sp1b200_machine; /* the machine's AIR constraints, uploaded once */
 
@@ -186,7 +186,7 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* machine, 
                               const uint32_t* h_gamma, const uint32_t* h_claims, uint32_t* h_challenger34, uint32_t* h_out,
                               uint64_t out_cap_words, uint64_t* h_out_words);
 
-/* ---- LogUp-GKR (replaces sp1-gpu/crates/logup_gkr + sys/lib/logup_gkr/*.cu) ---------------------------------------- */
+/* ---- LogUp-GKR (replaces sp1-gpu/crates/logup_gkr + sys/lib/logup_gkr/{all}.cu) ---------------------------------------- */
 
 /* The machine blob of sp1b200_machine_create may carry an interactions section after the AIR records
  * (crates/hypercube/src/lookup/interaction.rs:11-22; VirtualPairCol = sum weight * column + constant):

@@ -1,5 +1,8 @@
 // Context, memory and the kernel-level C entry points of include/sp1b200.h.
 #include "ctx.cuh"
+#include <atomic>
+#include <chrono>
+#include <cstring>
 #include <cstdarg>
 #include <cstring>
 #include <cstdlib>
@@ -85,6 +88,11 @@ sp1b200_err sp1b200_ctx_create(int device, const sp1b200_params* params, sp1b200
     SP1_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thresh = UINT64_MAX;
     SP1_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    SP1_CUDA(cudaHostAlloc((void**)&c->h_mail, (SP1_MAIL_HDR + SP1_MAIL_WORDS) * 4, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(c->h_mail, 0, (SP1_MAIL_HDR + SP1_MAIL_WORDS) * 4);
+    SP1_CUDA(cudaHostGetDevicePointer((void**)&c->d_mail, c->h_mail, 0));
+    SP1_CUDA(cudaMalloc((void**)&c->d_mail_counter, 64));
+    SP1_CUDA(cudaMemset(c->d_mail_counter, 0, 64));
     sp1b200_err e = sp1b200_init_tables(c);
     if (e) { delete c; return e; }
     SP1_CUDA(cudaStreamSynchronize(c->stream));
@@ -97,9 +105,36 @@ void sp1b200_ctx_destroy(sp1b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_TH); cudaFree(c->d_TL);
+    cudaFree(c->d_mail_counter);
+    if (c->h_mail) cudaFreeHost(c->h_mail);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
+}
+
+// Spin on the mailbox flag until the posting kernel with sequence number `seq` has published its payload.  The stream is
+// queried every few thousand spins so that a faulted kernel turns into an error instead of a hang.
+sp1b200_err sp1b200_mail_wait(sp1b200_ctx* c, uint32_t seq) {
+    volatile uint32_t* flag = c->h_mail;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint64_t spins = 0;; spins++) {
+        if (*flag == seq) { std::atomic_thread_fence(std::memory_order_acquire); return nullptr; }
+        if ((spins & 0x3fff) == 0x3fff) {
+            cudaError_t q = cudaStreamQuery(c->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return sp1b200_set_error("mail_wait: stream error: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && *flag != seq) {
+                // stream drained but the flag did not arrive: re-check once after a full fence, then fail loudly
+                std::atomic_thread_fence(std::memory_order_seq_cst);
+                if (*flag == seq) return nullptr;
+                return sp1b200_set_error("mail_wait: stream idle but sequence %u was never posted (flag = %u)", seq, *flag);
+            }
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 60.0)
+                return sp1b200_set_error("mail_wait: timed out waiting for sequence %u", seq);
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
 }
 
 sp1b200_err sp1b200_ctx_sync(sp1b200_ctx* c) { SP1_CUDA(cudaStreamSynchronize(c->stream)); return nullptr; }

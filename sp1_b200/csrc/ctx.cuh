@@ -4,6 +4,7 @@
 // sp1-gpu/crates/sys/lib/runtime/{stream,memory,mem_pool}.cu for this path.
 #pragma once
 #include <cuda_runtime.h>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -23,7 +24,40 @@ struct sp1b200_ctx {
     bool force_generic_ntt = false;  // SP1B200_GENERIC_NTT=1: reference (slow) kernels, used to cross-check the fast path
     std::map<std::string, float> phase_ms;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // mailbox: pinned + mapped host memory the round kernels write their few result words into, followed by a sequence flag;
+    // the host transcript polls the flag instead of issuing a copy + stream synchronise per sumcheck round
+    uint32_t* h_mail = nullptr;         // [0] flag, payload from MAIL_HDR
+    uint32_t* d_mail = nullptr;         // device alias of h_mail
+    uint32_t* d_mail_counter = nullptr; // device memory: blocks finished in the current posting kernel
+    uint32_t mail_seq = 0;
 };
+constexpr size_t SP1_MAIL_HDR = 16;               // words before the payload (64-byte aligned payload)
+constexpr size_t SP1_MAIL_WORDS = 1 << 16;        // payload capacity in words (256 KiB)
+
+struct Mail { uint32_t* flag; uint32_t* counter; uint32_t seq; };
+inline Mail sp1b200_mail_next(sp1b200_ctx* c) { return Mail{c->d_mail, c->d_mail_counter, ++c->mail_seq}; }
+inline uint32_t* sp1b200_mail_dev(sp1b200_ctx* c) { return c->d_mail + SP1_MAIL_HDR; }
+inline const uint32_t* sp1b200_mail_host(sp1b200_ctx* c) { return c->h_mail + SP1_MAIL_HDR; }
+extern "C" sp1b200_err sp1b200_mail_wait(sp1b200_ctx* c, uint32_t seq);
+
+#ifdef __CUDACC__
+// Last step of a posting kernel, called by EVERY thread after the block's payload words were stored through the device
+// alias: the last block to arrive publishes the sequence number (system-scope release) and re-arms the counter.
+__device__ __forceinline__ void sp1_mail_done(const Mail& m) {
+    if (!m.flag) return;  // launch-uniform: this launch does not post
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned prev = atomicAdd(m.counter, 1u);
+        if (prev == total - 1) {
+            *m.counter = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(m.flag) = m.seq;
+        }
+    }
+}
+#endif
 
 const char* sp1b200_set_error(const char* fmt, ...);
 
@@ -68,6 +102,18 @@ struct PhaseTimer {
         ctx->phase_ms[name] = ms;
     }
     ~PhaseTimer() { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+};
+
+// host wall-clock accumulator reported next to the CUDA-event phases (where the host waits or computes inside a phase)
+struct HostAccum {
+    sp1b200_ctx* ctx; const char* name; double ms = 0;
+    HostAccum(sp1b200_ctx* c, const char* n) : ctx(c), name(n) {}
+    ~HostAccum() { ctx->phase_ms[name] = (float)ms; }
+};
+struct HostSpan {
+    HostAccum& a; std::chrono::steady_clock::time_point t0;
+    explicit HostSpan(HostAccum& acc) : a(acc), t0(std::chrono::steady_clock::now()) {}
+    ~HostSpan() { a.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
 // resolves a host-or-device pointer to a device pointer, staging through a temporary if needed

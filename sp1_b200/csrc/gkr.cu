@@ -142,7 +142,7 @@ __device__ __forceinline__ void pair_sums(const Row4& x, const Row4& y, const Ex
     se = kb::ext_add(se, kb::ext_mul(e, ers));
 }
 
-__device__ __forceinline__ void block_reduce3(Ext a, Ext b, Ext c, uint32_t* __restrict__ partial) {
+__device__ __forceinline__ void block_reduce3(Ext a, Ext b, Ext c, uint32_t* __restrict__ partial, const Mail& mail) {
     __shared__ uint32_t red[12][256];
     for (int l = 0; l < 4; l++) { red[l][threadIdx.x] = a.c[l]; red[4 + l][threadIdx.x] = b.c[l]; red[8 + l][threadIdx.x] = c.c[l]; }
     __syncthreads();
@@ -152,12 +152,13 @@ __device__ __forceinline__ void block_reduce3(Ext a, Ext b, Ext c, uint32_t* __r
         __syncthreads();
     }
     if (threadIdx.x < 12) partial[blockIdx.x * 12 + threadIdx.x] = red[threadIdx.x][0];
+    sp1_mail_done(mail);  // `partial` is the mailbox payload: the host transcript polls the flag (ctx.cuh)
 }
 
 // round 0 of a layer: sums straight from the fraction sequence. work item = (chip, k, row pair i)
 __global__ void __launch_bounds__(256) gkr_sum_seq_kernel(JobTable jobs, const uint32_t* __restrict__ num, const uint32_t* __restrict__ den,
                                                           const uint32_t* __restrict__ eq_int, const uint32_t* __restrict__ eq_row, Ext lambda,
-                                                          uint32_t* __restrict__ partial) {
+                                                          uint32_t* __restrict__ partial, Mail mail) {
     Ext s0 = kb::ext_zero(), sh = kb::ext_zero(), se = kb::ext_zero();
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < jobs.total; w += (uint64_t)gridDim.x * blockDim.x) {
         const ChipJob& c = jobs.j[find_job(jobs, w)];
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(256) gkr_sum_seq_kernel(JobTable jobs, const u
         Row4 x = row_from_seq(num, den, base, c.rows_in, 2 * i), y = row_from_seq(num, den, base, c.rows_in, 2 * i + 1);
         pair_sums(x, y, ldE(eq_int, c.int_off + k), ldE(eq_row, 2 * i), ldE(eq_row, 2 * i + 1), lambda, s0, sh, se);
     }
-    block_reduce3(s0, sh, se, partial);
+    block_reduce3(s0, sh, se, partial, mail);
 }
 
 // fix the last row variable (input = fraction sequence or working arrays), write the working arrays of the next round and
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(256) gkr_sum_seq_kernel(JobTable jobs, const u
 template <bool FROM_SEQ>
 __global__ void __launch_bounds__(256) gkr_fix_sum_kernel(JobTable jobs, const uint32_t* __restrict__ in_a, const uint32_t* __restrict__ in_b,
                                                           uint32_t* __restrict__ out, const uint32_t* __restrict__ eq_int,
-                                                          const uint32_t* __restrict__ eq_row_new, Ext alpha, Ext lambda, uint32_t* __restrict__ partial) {
+                                                          const uint32_t* __restrict__ eq_row_new, Ext alpha, Ext lambda, uint32_t* __restrict__ partial,
+                                                          Mail mail) {
     Ext s0 = kb::ext_zero(), sh = kb::ext_zero(), se = kb::ext_zero();
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < jobs.total; w += (uint64_t)gridDim.x * blockDim.x) {
         const ChipJob& c = jobs.j[find_job(jobs, w)];
@@ -205,7 +207,62 @@ __global__ void __launch_bounds__(256) gkr_fix_sum_kernel(JobTable jobs, const u
         }
         pair_sums(nr[0], nr[1], ldE(eq_int, c.int_off + k), ldE(eq_row_new, 2 * i), ldE(eq_row_new, 2 * i + 1), lambda, s0, sh, se);
     }
-    block_reduce3(s0, sh, se, partial);
+    block_reduce3(s0, sh, se, partial, mail);
+}
+
+// ---- interaction variables (logup_poly.rs:118-176 + the generic round of sumcheck/src/prover.rs) -------------------------------
+// After the last row variable every (chip, interaction) holds one row; the layer becomes four arrays over the padded
+// interaction index (numerator 0 / denominator 1 beyond the machine's interactions), plus the eq table over that index.
+// arr = [5][n] EF: n0 | n1 | d0 | d1 | eq.
+__global__ void __launch_bounds__(256) gkr_flatten_kernel(JobTable jobs, const uint32_t* __restrict__ work, const uint32_t* __restrict__ eq_int,
+                                                          uint32_t n, uint32_t* __restrict__ arr, uint32_t* __restrict__ payload, Mail mail) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        Ext n0 = kb::ext_zero(), n1 = kb::ext_zero(), d0 = kb::ext_one(), d1 = kb::ext_one();
+        for (int q = 0; q < jobs.n; q++) {
+            const ChipJob& c = jobs.j[q];
+            if (t >= c.int_off && t < c.int_off + c.I) {
+                const uint64_t o = c.in_off + (t - c.int_off), sI = c.I;  // one row per interaction: [4][I][1]
+                n0 = ldE(work, o); d0 = ldE(work, o + sI); n1 = ldE(work, o + 2 * sI); d1 = ldE(work, o + 3 * sI);
+            }
+        }
+        stE(arr, t, n0); stE(arr, (uint64_t)n + t, n1); stE(arr, 2ull * n + t, d0); stE(arr, 3ull * n + t, d1);
+        stE(arr, 4ull * n + t, ldE(eq_int, t));
+        if (n == 1) { stE(payload, 3, n0); stE(payload, 5, n1); stE(payload, 7, d0); stE(payload, 9, d1); }
+    }
+    if (mail.flag) sp1_mail_done(mail);
+}
+// One interaction round in one block: (optionally) bind the previous variable with alpha, store the halved arrays, and post
+// (eval_0, eval_half, eq_sum) of the next variable.  When two entries remain they are posted too (payload EF slots 3..10:
+// n0[0] n0[1] n1[0] n1[1] d0[0] d0[1] d1[0] d1[1]) so that the host can finish the layer without another launch.
+__global__ void __launch_bounds__(256) gkr_inter_round_kernel(const uint32_t* __restrict__ in, uint32_t n_in, int fold, Ext alpha, Ext lambda,
+                                                              uint32_t* __restrict__ out, uint32_t* __restrict__ payload, Mail mail) {
+    const uint32_t n_cur = fold ? n_in / 2 : n_in;
+    Ext s0 = kb::ext_zero(), sh = kb::ext_zero(), se = kb::ext_zero();
+    for (uint32_t j = threadIdx.x; j < n_cur / 2; j += blockDim.x) {
+        Ext v[5][2];
+#pragma unroll
+        for (int a = 0; a < 5; a++)
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const uint32_t x = 2 * j + hh;
+                if (fold) {
+                    const Ext lo = ldE(in, (uint64_t)a * n_in + 2 * x), hi = ldE(in, (uint64_t)a * n_in + 2 * x + 1);
+                    v[a][hh] = kb::ext_add(lo, kb::ext_mul(alpha, kb::ext_sub(hi, lo)));
+                    stE(out, (uint64_t)a * n_cur + x, v[a][hh]);
+                } else v[a][hh] = ldE(in, (uint64_t)a * n_in + x);
+            }
+        const Ext &n0a = v[0][0], &n1a = v[1][0], &d0a = v[2][0], &d1a = v[3][0], &ea = v[4][0], &eb = v[4][1];
+        s0 = kb::ext_add(s0, kb::ext_mul(ea, kb::ext_add(kb::ext_mul(lambda, kb::ext_add(kb::ext_mul(d0a, n1a), kb::ext_mul(d1a, n0a))), kb::ext_mul(d0a, d1a))));
+        const Ext N0 = kb::ext_add(v[0][0], v[0][1]), N1 = kb::ext_add(v[1][0], v[1][1]), D0 = kb::ext_add(v[2][0], v[2][1]), D1 = kb::ext_add(v[3][0], v[3][1]);
+        const Ext es = kb::ext_add(ea, eb);
+        sh = kb::ext_add(sh, kb::ext_mul(es, kb::ext_add(kb::ext_mul(lambda, kb::ext_add(kb::ext_mul(D0, N1), kb::ext_mul(D1, N0))), kb::ext_mul(D0, D1))));
+        se = kb::ext_add(se, es);
+        if (n_cur == 2) {
+#pragma unroll
+            for (int a = 0; a < 4; a++) { stE(payload, 3 + 2 * a, v[a][0]); stE(payload, 4 + 2 * a, v[a][1]); }
+        }
+    }
+    block_reduce3(s0, sh, se, payload, mail);
 }
 
 __global__ void gkr_eq_table_kernel(const uint32_t* __restrict__ point, int k, uint32_t* __restrict__ E) {

@@ -42,16 +42,25 @@ struct E4 {
 inline E4 operator+(const E4& a, const E4& b) { E4 r; for (int i = 0; i < 4; i++) r.c[i] = add(a.c[i], b.c[i]); return r; }
 inline E4 operator-(const E4& a, const E4& b) { E4 r; for (int i = 0; i < 4; i++) r.c[i] = sub(a.c[i], b.c[i]); return r; }
 inline E4 operator*(const E4& a, uint32_t s) { E4 r; for (int i = 0; i < 4; i++) r.c[i] = mul(a.c[i], s); return r; }
+// x < 2 p 2^32 (a sum of up to four products of canonical values) -> canonical x 2^-32 mod p; subtractive Montgomery form
+inline uint32_t reduce4(uint64_t x) {
+    uint32_t hi = (uint32_t)(x >> 32);
+    if (hi >= P) hi -= P;
+    const uint32_t m = (uint32_t)x * 0x81000001u;  // lo(x) * p^-1 mod 2^32
+    const uint32_t q = (uint32_t)(((uint64_t)m * P) >> 32);
+    return hi >= q ? hi - q : hi + P - q;
+}
 inline E4 operator*(const E4& a, const E4& b) {
-    uint32_t t[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) t[i + j] = add(t[i + j], mul(a.c[i], b.c[j]));
-    const uint32_t three = to_monty(3);
+    // x^4 = 3 folded into b: every coefficient is one sum of four 62-bit products and one reduction (same form as kb::ext_mul)
+    auto tri = [](uint32_t v) { return add(add(v, v), v); };
+    const uint64_t a0 = a.c[0], a1 = a.c[1], a2 = a.c[2], a3 = a.c[3];
+    const uint64_t b0 = b.c[0], b1 = b.c[1], b2 = b.c[2], b3 = b.c[3];
+    const uint64_t t1 = tri(b.c[1]), t2 = tri(b.c[2]), t3 = tri(b.c[3]);
     E4 r;
-    r.c[0] = add(t[0], mul(three, t[4]));
-    r.c[1] = add(t[1], mul(three, t[5]));
-    r.c[2] = add(t[2], mul(three, t[6]));
-    r.c[3] = t[3];
+    r.c[0] = reduce4(a0 * b0 + a1 * t3 + a2 * t2 + a3 * t1);
+    r.c[1] = reduce4(a0 * b1 + a1 * b0 + a2 * t3 + a3 * t2);
+    r.c[2] = reduce4(a0 * b2 + a1 * b1 + a2 * b0 + a3 * t3);
+    r.c[3] = reduce4(a0 * b3 + a1 * b2 + a2 * b1 + a3 * b0);
     return r;
 }
 inline E4 inv(const E4& a) {

@@ -127,7 +127,7 @@ __device__ __forceinline__ uint32_t seg_load(const SegTable& t, uint64_t i) {
     return 0;
 }
 
-__device__ __forceinline__ void block_reduce2(Ext a, Ext b, uint32_t* __restrict__ partial) {
+__device__ __forceinline__ void block_reduce2(Ext a, Ext b, uint32_t* __restrict__ partial, const Mail& mail) {
     __shared__ uint32_t red[8][256];
     for (int l = 0; l < 4; l++) { red[l][threadIdx.x] = a.c[l]; red[4 + l][threadIdx.x] = b.c[l]; }
     __syncthreads();
@@ -137,11 +137,12 @@ __device__ __forceinline__ void block_reduce2(Ext a, Ext b, uint32_t* __restrict
         __syncthreads();
     }
     if (threadIdx.x < 8) partial[blockIdx.x * 8 + threadIdx.x] = red[threadIdx.x][0];
+    sp1_mail_done(mail);  // `partial` is the mailbox payload (ctx.cuh): the host transcript polls instead of copy + synchronise
 }
 
 // round 0: sum_j ext[2j]*base[2j]  and  sum_j (ext[2j]+ext[2j+1]) * (base[2j]+base[2j+1])   (base in F)
 __global__ void __launch_bounds__(256) hadamard_sum0_kernel(SegTable base, const uint32_t* __restrict__ ext, uint64_t npairs,
-                                                            uint32_t* __restrict__ partial) {
+                                                            uint32_t* __restrict__ partial, Mail mail) {
     Ext s0 = kb::ext_zero(), sh = kb::ext_zero();
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < npairs; j += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t b0 = seg_load(base, 2 * j), b1 = seg_load(base, 2 * j + 1);
@@ -149,13 +150,13 @@ __global__ void __launch_bounds__(256) hadamard_sum0_kernel(SegTable base, const
         s0 = kb::ext_add(s0, kb::ext_mul_base(e0, b0));
         sh = kb::ext_add(sh, kb::ext_mul_base(kb::ext_add(e0, e1), kb::add(b0, b1)));
     }
-    block_reduce2(s0, sh, partial);
+    block_reduce2(s0, sh, partial, mail);
 }
 
 // fix the last variable of round 0 (base F -> EF) and accumulate round-1 sums
 __global__ void __launch_bounds__(256) hadamard_fold0_kernel(SegTable base, const uint32_t* __restrict__ ext, uint64_t nout_pairs, Ext alpha,
                                                              uint32_t* __restrict__ base_out, uint32_t* __restrict__ ext_out,
-                                                             uint32_t* __restrict__ partial, uint64_t nout) {
+                                                             uint32_t* __restrict__ partial, uint64_t nout, Mail mail) {
     Ext s0 = kb::ext_zero(), sh = kb::ext_zero();
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nout_pairs; j += (uint64_t)gridDim.x * blockDim.x) {
         Ext nb[2], ne[2];
@@ -174,13 +175,13 @@ __global__ void __launch_bounds__(256) hadamard_fold0_kernel(SegTable base, cons
         s0 = kb::ext_add(s0, kb::ext_mul(ne[0], nb[0]));
         sh = kb::ext_add(sh, kb::ext_mul(kb::ext_add(ne[0], ne[1]), kb::ext_add(nb[0], nb[1])));
     }
-    block_reduce2(s0, sh, partial);
+    block_reduce2(s0, sh, partial, mail);
 }
 
 // rounds >= 1: fix the last variable (EF -> EF) and accumulate the next round's sums
 __global__ void __launch_bounds__(256) hadamard_fold_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ ext,
                                                             uint64_t nout_pairs, Ext alpha, uint32_t* __restrict__ base_out,
-                                                            uint32_t* __restrict__ ext_out, uint32_t* __restrict__ partial, uint64_t nout) {
+                                                            uint32_t* __restrict__ ext_out, uint32_t* __restrict__ partial, uint64_t nout, Mail mail) {
     Ext s0 = kb::ext_zero(), sh = kb::ext_zero();
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nout_pairs; j += (uint64_t)gridDim.x * blockDim.x) {
         Ext nb[2], ne[2];
@@ -194,12 +195,13 @@ __global__ void __launch_bounds__(256) hadamard_fold_kernel(const uint32_t* __re
                 ne[h] = kb::ext_add(e0, kb::ext_mul(alpha, kb::ext_sub(e1, e0)));
                 kb::ext_store(base_out + 4 * o, nb[h]);
                 kb::ext_store(ext_out + 4 * o, ne[h]);
+                if (nout == 1) kb::ext_store(partial + 8, nb[h]);  // last round: the dense component evaluation rides along
             } else { nb[h] = kb::ext_zero(); ne[h] = kb::ext_zero(); }
         }
         s0 = kb::ext_add(s0, kb::ext_mul(ne[0], nb[0]));
         sh = kb::ext_add(sh, kb::ext_mul(kb::ext_add(ne[0], ne[1]), kb::ext_add(nb[0], nb[1])));
     }
-    block_reduce2(s0, sh, partial);
+    block_reduce2(s0, sh, partial, mail);
 }
 
 // ---- branching program (slop/crates/jagged/src/poly.rs:136-175, 384-470) ---------------------------------------
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(128) bp_round2_kernel(const uint8_t* __restric
                                                         const uint32_t* __restrict__ rho_by_pos, const uint32_t* __restrict__ ri_eq,
                                                         const uint32_t* __restrict__ zc, const uint32_t* __restrict__ inter,
                                                         const uint32_t* __restrict__ P, const uint32_t* __restrict__ T, Ext half,
-                                                        uint32_t* __restrict__ partial) {
+                                                        uint32_t* __restrict__ partial, Mail mail) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     Ext v = kb::ext_zero();
     const uint32_t k = t >> 1, node = t & 1;
@@ -406,6 +408,7 @@ __global__ void __launch_bounds__(128) bp_round2_kernel(const uint8_t* __restric
         __syncthreads();
     }
     if (threadIdx.x < 8) partial[blockIdx.x * 8 + threadIdx.x] = red[threadIdx.x & 3][threadIdx.x >> 2];
+    sp1_mail_done(mail);
 }
 // after round r's challenge: bind position split = dim-1-r: rho_by_pos, inter[k] *= eq(alpha, bit), P_k <- P_k M_layer(bound)
 // (at the switch to the second half P_k restarts at e0^T: the caller rebuilds T with the bound next-coordinates first)
@@ -454,6 +457,14 @@ sp1b200_err sum_partials(sp1b200_ctx* ctx, const uint32_t* d_partial, unsigned n
     std::vector<uint32_t> h((size_t)nblk * 8);
     SP1_CUDA(cudaMemcpyAsync(h.data(), d_partial, h.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     SP1_CUDA(cudaStreamSynchronize(ctx->stream));
+    a = E4(); b = E4();
+    for (unsigned k = 0; k < nblk; k++) { a = a + E4::load(&h[8 * k]); b = b + E4::load(&h[8 * k + 4]); }
+    return nullptr;
+}
+// same sums from the mailbox payload of the posting kernel with sequence number `seq` (8 words per block)
+sp1b200_err sum_mail(sp1b200_ctx* ctx, uint32_t seq, unsigned nblk, E4& a, E4& b) {
+    SP1_TRY(sp1b200_mail_wait(ctx, seq));
+    const uint32_t* h = sp1b200_mail_host(ctx);
     a = E4(); b = E4();
     for (unsigned k = 0; k < nblk; k++) { a = a + E4::load(&h[8 * k]); b = b + E4::load(&h[8 * k + 4]); }
     return nullptr;
@@ -597,7 +608,8 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
     SP1_TRY(mem.alloc((void**)&d_b, (N / 2) * 16));
     SP1_TRY(mem.alloc((void**)&d_b2, (N / 4 + 1) * 16));
     const unsigned MAXB = 148 * 8;
-    SP1_TRY(mem.alloc((void**)&d_partial, (size_t)MAXB * 32 + 4096));
+    static_assert(148 * 8 * 8 + 16 <= SP1_MAIL_WORDS, "round partials must fit the mailbox payload");
+    d_partial = sp1b200_mail_dev(ctx);  // the round kernels post their block partials straight into the mailbox
     {
         PhaseTimer t(ctx, "jagged.little_poly");
         SP1_LAUNCH(ctx, jagged_poly_kernel, blocks_for(N), 256, 0, d_prefix, (uint32_t)total_cols, d_coleq, d_roweq, N, d_ext);
@@ -615,16 +627,18 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
     auto grid_for = [&](uint64_t n) { unsigned g = blocks_for(n); return g > MAXB ? MAXB : (g ? g : 1u); };
     uint32_t *cur_b = nullptr, *cur_e = d_ext, *nxt_b = d_b, *nxt_e = d_ext2;
     unsigned prev_g = 0;
+    uint32_t prev_seq = 0;
     for (uint32_t rd = 0; rd < lm; rd++) {
         const uint64_t n = N >> rd;  // current length
         E4 e0, eh;
         unsigned g;
         if (rd == 0) {
             g = grid_for(n / 2);
-            SP1_LAUNCH(ctx, hadamard_sum0_kernel, g, 256, 0, seg, cur_e, n / 2, d_partial);
-            SP1_TRY(sum_partials(ctx, d_partial, g, e0, eh));
+            const Mail mail = sp1b200_mail_next(ctx);
+            SP1_LAUNCH(ctx, hadamard_sum0_kernel, g, 256, 0, seg, cur_e, n / 2, d_partial, mail);
+            SP1_TRY(sum_mail(ctx, mail.seq, g, e0, eh));
         } else {
-            SP1_TRY(sum_partials(ctx, d_partial, prev_g, e0, eh));  // accumulated by the previous fold launch
+            SP1_TRY(sum_mail(ctx, prev_seq, prev_g, e0, eh));  // accumulated by the previous fold launch
         }
         E4 e1 = round_claim - e0;
         E4 c[3];
@@ -640,21 +654,22 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
         const uint64_t nout = n / 2;
         Ext da{{alpha.c[0], alpha.c[1], alpha.c[2], alpha.c[3]}};
         g = grid_for((nout + 1) / 2);
+        const Mail mail = sp1b200_mail_next(ctx); prev_seq = mail.seq;
         if (rd == 0) {
-            SP1_LAUNCH(ctx, hadamard_fold0_kernel, g, 256, 0, seg, cur_e, (nout + 1) / 2, da, nxt_b, nxt_e, d_partial, nout);
+            SP1_LAUNCH(ctx, hadamard_fold0_kernel, g, 256, 0, seg, cur_e, (nout + 1) / 2, da, nxt_b, nxt_e, d_partial, nout, mail);
             cur_b = nxt_b; cur_e = nxt_e; nxt_b = d_b2; nxt_e = d_ext;  // d_ext (N entries) is free again
         } else {
-            SP1_LAUNCH(ctx, hadamard_fold_kernel, g, 256, 0, cur_b, cur_e, (nout + 1) / 2, da, nxt_b, nxt_e, d_partial, nout);
+            SP1_LAUNCH(ctx, hadamard_fold_kernel, g, 256, 0, cur_b, cur_e, (nout + 1) / 2, da, nxt_b, nxt_e, d_partial, nout, mail);
             std::swap(cur_b, nxt_b); std::swap(cur_e, nxt_e);
         }
         prev_g = g;
     }
     // component evaluations: base[0] (the dense trace at the sumcheck point), ext[0]
-    uint32_t base_eval_w[4];
-    SP1_CUDA(cudaMemcpyAsync(base_eval_w, cur_b, 16, cudaMemcpyDeviceToHost, st));
-    SP1_CUDA(cudaStreamSynchronize(st));
+    // (posted by the last fold launch next to its, unused, partial sums: payload EF slot 2)
+    if (lm < 2) return sp1b200_set_error("jagged_prove: fewer than two sumcheck variables (log_m = %u)", lm);
+    SP1_TRY(sp1b200_mail_wait(ctx, prev_seq));
+    const E4 base_eval = E4::load(sp1b200_mail_host(ctx) + 8);
     t_sc.stop();
-    const E4 base_eval = E4::load(base_eval_w);
 
     // ---- jagged evaluation (branching program) sumcheck --------------------------------------------------------------
     std::vector<uint32_t> je_words;
@@ -718,11 +733,15 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
             SP1_CUDA(cudaMemsetAsync(d_rho_pos, 0, (size_t)dim * 16, st));
         }
         SP1_LAUNCH(ctx, bp_suffix_kernel, blocks_for(nk, 128), 128, 0, d_bits, nk, dim, 0, d_rho_pos, d_ri, d_T);
+        const bool bp_mail = (size_t)nblk * 8 <= SP1_MAIL_WORDS;  // otherwise fall back to copy + synchronise
         for (uint32_t round = 0; round < dim; round++) {
             if (round == hl) SP1_LAUNCH(ctx, bp_suffix_kernel, blocks_for(nk, 128), 128, 0, d_bits, nk, dim, 1, d_rho_pos, d_ri, d_T);
-            SP1_LAUNCH(ctx, bp_round2_kernel, nblk, 128, 0, d_bits, nk, dim, round, d_rho_pos, d_ri, d_zc, d_inter, d_P, d_T, dhalf, d_part);
+            const Mail mail = sp1b200_mail_next(ctx);
+            SP1_LAUNCH(ctx, bp_round2_kernel, nblk, 128, 0, d_bits, nk, dim, round, d_rho_pos, d_ri, d_zc, d_inter, d_P, d_T, dhalf,
+                       bp_mail ? sp1b200_mail_dev(ctx) : d_part, bp_mail ? mail : Mail{nullptr, nullptr, 0});
             E4 y0, yh;
-            SP1_TRY(sum_partials(ctx, d_part, nblk, y0, yh));
+            if (bp_mail) SP1_TRY(sum_mail(ctx, mail.seq, nblk, y0, yh));
+            else SP1_TRY(sum_partials(ctx, d_part, nblk, y0, yh));
             E4 y1 = cl - y0;
             E4 c[3];
             interp_0_1_half(y0, y1, yh, c);

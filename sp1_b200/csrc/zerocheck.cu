@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(ZC_BLOCK) zc_sum_kernel(const ZcJob* __restric
 }
 
 // out[(job * 3 + node) * 3 + slot] = sum over the job's blocks
-__global__ void __launch_bounds__(128) zc_reduce_kernel(const ZcJob* __restrict__ jobs, const uint32_t* __restrict__ partial, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(128) zc_reduce_kernel(const ZcJob* __restrict__ jobs, const uint32_t* __restrict__ partial, uint32_t* __restrict__ out,
+                                                        Mail mail) {
     const ZcJob job = jobs[blockIdx.x];
     __shared__ uint32_t red[36][4];
     const int slot = threadIdx.x >> 2, part = threadIdx.x & 3;  // 32 groups of 4 threads; 36 words = 9 ext -> loop
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(128) zc_reduce_kernel(const ZcJob* __restrict_
         const uint32_t* r = red[threadIdx.x];
         out[blockIdx.x * 36 + threadIdx.x] = kb::add(kb::add(r[0], r[1]), kb::add(r[2], r[3]));
     }
+    sp1_mail_done(mail);  // `out` is the mailbox payload: the host polls the flag instead of copy + synchronise
 }
 
 // out[j][i] = in[j][2i] + alpha (in[j][2i+1] - in[j][2i]),  i < ceil(h/2)   (column-major, EF out; main columns then preprocessed)
@@ -497,7 +499,8 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     if (!jobs.empty()) SP1_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(ZcJob), cudaMemcpyHostToDevice, st));
     if (!fjobs.empty()) SP1_CUDA(cudaMemcpyAsync(d_fjobs, fjobs.data(), fjobs.size() * sizeof(ZcFixJob), cudaMemcpyHostToDevice, st));
     SP1_TRY(mem.alloc((void**)&d_partial, (size_t)max_blocks * 36 * 4));
-    SP1_TRY(mem.alloc((void**)&d_sums, (size_t)max_jobs * 36 * 4));
+    if ((size_t)max_jobs * 36 > SP1_MAIL_WORDS) return sp1b200_set_error("zerocheck: %u chips exceed the mailbox payload", max_jobs);
+    d_sums = sp1b200_mail_dev(ctx);
     SP1_CUDA(cudaMemsetAsync(d_final, 0, (wsum ? wsum : 1) * 16, st));
     auto launch_sum = [&](const Launch& Lc, bool ext, int first, uint32_t* part) -> sp1b200_err {
         dim3 g(Lc.blocks, 3, 1);
@@ -526,15 +529,16 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
         const RoundPlan& R = plan[rd];
         // every chip's partial sums: one launch per register-file tier, one reduction each, one copy back
         {
-            uint32_t blk = 0; size_t jb = 0;
+            uint32_t blk = 0, seq = 0; size_t jb = 0;
             for (const Launch& Lc : R.sums) {
                 SP1_TRY(launch_sum(Lc, rd > 0, rd == 0, d_partial + (size_t)blk * 36));
-                SP1_LAUNCH(ctx, zc_reduce_kernel, Lc.n_jobs, 128, 0, d_jobs + Lc.job0, d_partial + (size_t)blk * 36, d_sums + jb * 36);
+                const Mail mail = sp1b200_mail_next(ctx); seq = mail.seq;
+                SP1_LAUNCH(ctx, zc_reduce_kernel, Lc.n_jobs, 128, 0, d_jobs + Lc.job0, d_partial + (size_t)blk * 36, d_sums + jb * 36, mail);
                 blk += Lc.blocks; jb += Lc.n_jobs;
             }
-            if (jb) {
-                SP1_CUDA(cudaMemcpyAsync(hs.data(), d_sums, jb * 36 * 4, cudaMemcpyDeviceToHost, st));
-                SP1_CUDA(cudaStreamSynchronize(st));
+            if (jb) {  // launches complete in stream order: the last sequence number covers every tier
+                SP1_TRY(sp1b200_mail_wait(ctx, seq));
+                memcpy(hs.data(), sp1b200_mail_host(ctx), jb * 36 * 4);
             }
         }
         std::fill(job_of_chip.begin(), job_of_chip.end(), -1);

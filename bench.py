@@ -188,7 +188,7 @@ def main():
     padded_cells = ((cells + (1 << 21) - 1) >> 21) << 21
 
     phase_names = ["commit.rs_encode", "commit.merkle", "shard.commit", "gkr.circuit", "gkr.rounds", "gkr.openings", "gkr.total", "gkr.host_wait", "gkr.host_interaction", "gkr.host_transcript",
-                   "zerocheck.total", "jagged.little_poly", "jagged.sumcheck", "jagged.eval_sumcheck", "open.batch", "open.fri_rounds",
+                   "zerocheck.total", "zerocheck.host_wait", "zerocheck.host_math", "zerocheck.host_setup", "jagged.little_poly", "jagged.sumcheck", "jagged.eval_sumcheck", "open.batch", "open.fri_rounds",
                    "open.queries", "open.total", "jagged.total", "shard.total"]
     acc = {}
 

@@ -116,6 +116,12 @@ void sp1b200_ctx_destroy(sp1b200_ctx* c) {
 // queried every few thousand spins so that a faulted kernel turns into an error instead of a hang.
 sp1b200_err sp1b200_mail_wait(sp1b200_ctx* c, uint32_t seq) {
     volatile uint32_t* flag = c->h_mail;
+    static const bool no_poll = [] { const char* e = getenv("SP1B200_MAIL_SYNC"); return e && e[0] == '1'; }();
+    if (no_poll) {  // profiling aid: wait with a stream synchronise instead of spinning (tools that serialise launches)
+        SP1_CUDA(cudaStreamSynchronize(c->stream));
+        if (*flag != seq) return sp1b200_set_error("mail_wait: sequence %u was not posted (flag = %u)", seq, *flag);
+        return nullptr;
+    }
     const auto t0 = std::chrono::steady_clock::now();
     for (uint64_t spins = 0;; spins++) {
         if (*flag == seq) { std::atomic_thread_fence(std::memory_order_acquire); return nullptr; }

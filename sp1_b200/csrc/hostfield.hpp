@@ -21,7 +21,7 @@ inline uint32_t add(uint32_t a, uint32_t b) { uint32_t s = a + b; return s >= P 
 inline uint32_t sub(uint32_t a, uint32_t b) { return a >= b ? a - b : a + P - b; }
 inline uint32_t neg(uint32_t a) { return a ? P - a : 0; }
 inline uint32_t mul(uint32_t a, uint32_t b) { return reduce((uint64_t)a * b); }
-inline uint32_t to_monty(uint64_t c) { return (uint32_t)(((c % P) << 32) % P); }
+constexpr uint32_t to_monty(uint64_t c) { return (uint32_t)(((c % P) << 32) % P); }
 inline uint32_t from_monty(uint32_t m) { return reduce(m); }
 inline uint32_t pow(uint32_t b, uint64_t e) {
     uint32_t r = ONE;
@@ -90,6 +90,38 @@ inline std::vector<E4> partial_lagrange(const std::vector<E4>& point) {
     }
     return ev;
 }
+
+// Lagrange basis over N distinct nodes, L[i][k] = coefficient of X^k in L_i(X) (degree N-1), with ONE field inversion
+// (Montgomery's trick) and no allocation: the transcript drivers call this once per sumcheck round.
+template <int N> inline void lagrange_basis(const E4 (&x)[N], E4 (&L)[N][N]) {
+    // P(X) = prod_j (X - x_j), monic of degree N
+    E4 p[N + 1];
+    p[0] = E4::one();
+    for (int j = 0; j < N; j++) {           // multiply by (X - x_j)
+        p[j + 1] = p[j];
+        for (int k = j; k >= 1; k--) p[k] = p[k - 1] - p[k] * x[j];
+        p[0] = E4() - p[0] * x[j];
+    }
+    // den_i = prod_{j != i} (x_i - x_j), all inverted with one inversion
+    E4 den[N], pre[N];
+    for (int i = 0; i < N; i++) {
+        E4 d = E4::one();
+        for (int j = 0; j < N; j++) if (j != i) d = d * (x[i] - x[j]);
+        den[i] = d;
+    }
+    pre[0] = den[0];
+    for (int i = 1; i < N; i++) pre[i] = pre[i - 1] * den[i];
+    E4 acc = inv(pre[N - 1]);
+    for (int i = N - 1; i >= 0; i--) {
+        const E4 di = i ? acc * pre[i - 1] : acc;  // 1 / den_i
+        acc = acc * den[i];
+        // Q_i(X) = P(X) / (X - x_i) by synthetic division, scaled by 1/den_i
+        E4 q = E4::one();                    // coefficient of X^(N-1)
+        L[i][N - 1] = di;
+        for (int k = N - 1; k >= 1; k--) { q = p[k] + x[i] * q; L[i][k - 1] = q * di; }
+    }
+}
+template <int N> inline E4 eval_poly(const E4 (&c)[N], const E4& x) { E4 r; for (int i = N; i-- > 0;) r = r * x + c[i]; return r; }
 
 inline unsigned log2_ceil(uint64_t n) { unsigned k = 0; while (((uint64_t)1 << k) < n) k++; return k; }
 

@@ -27,7 +27,7 @@ using kb::Ext;
 using hf::E4;
 
 constexpr int ZC_BLOCK = 128;
-constexpr int ZC_LOCAL_REGS = 256;  // fallback tier: register file in local memory
+constexpr int ZC_LOCAL_REGS = 128;  // fallback tier: register file in local memory
 
 template <class K> struct Ops;
 template <> struct Ops<uint32_t> {
@@ -49,19 +49,6 @@ template <> struct Ops<Ext> {
     static __device__ __forceinline__ Ext scale(const Ext& e, const Ext& k) { return kb::ext_mul(e, k); }
 };
 
-// value of column `col` at node t in {0,2,4} on row pair i:  z + t (o - z), o = 0 past the last real row
-template <class K>
-__device__ __forceinline__ K interp_pair(const K* __restrict__ base, uint32_t col, uint64_t h, uint64_t i, int node) {
-    using O = Ops<K>;
-    const K* c = base + (uint64_t)col * h;
-    K z = O::load(c, 2 * i);
-    if (node == 0) return z;
-    K o = (2 * i + 1 < h) ? O::load(c, 2 * i + 1) : O::zero();
-    K d = O::sub(o, z);
-    K d2 = O::add(d, d);
-    return node == 1 ? O::add(z, d2) : O::add(z, O::add(d2, d2));
-}
-
 // one chip in one round
 struct ZcJob {
     const void* main; const void* prep; const uint32_t* alpha_pows; uint64_t h;
@@ -82,102 +69,158 @@ __device__ __forceinline__ int find_job(const J* __restrict__ jobs, int n, uint3
     return lo;
 }
 
-// register file: shared memory [reg][thread] (SMEM) or a local array (fallback for programs whose pressure does not fit)
+// register file: every register holds the value at ALL THREE evaluation nodes (the program is decoded once per row pair and
+// the three evaluations run in lockstep: one instruction fetch, three independent products in flight, one pass over the
+// columns).  Shared memory [reg][node][thread] (SMEM), or a local array for programs whose pressure does not fit.
 template <class K, bool SMEM> struct RegFile;
 template <class K> struct RegFile<K, true> {
     K* base;
     __device__ __forceinline__ RegFile(unsigned char* smem) : base(reinterpret_cast<K*>(smem) + threadIdx.x) {}
-    __device__ __forceinline__ K get(uint32_t r) const { return base[r * ZC_BLOCK]; }
-    __device__ __forceinline__ void set(uint32_t r, const K& v) { base[r * ZC_BLOCK] = v; }
+    __device__ __forceinline__ K get(uint32_t r, int n) const { return base[(r * 3 + n) * ZC_BLOCK]; }
+    __device__ __forceinline__ void set(uint32_t r, int n, const K& v) { base[(r * 3 + n) * ZC_BLOCK] = v; }
 };
 template <class K> struct RegFile<K, false> {
-    K regs[ZC_LOCAL_REGS];
+    K regs[ZC_LOCAL_REGS * 3];
     __device__ __forceinline__ RegFile(unsigned char*) {}
-    __device__ __forceinline__ K get(uint32_t r) const { return regs[r]; }
-    __device__ __forceinline__ void set(uint32_t r, const K& v) { regs[r] = v; }
+    __device__ __forceinline__ K get(uint32_t r, int n) const { return regs[r * 3 + n]; }
+    __device__ __forceinline__ void set(uint32_t r, int n, const K& v) { regs[r * 3 + n] = v; }
 };
+
+// column values at the nodes t = 0, 2, 4 of row pair i:  z, z + 2d, z + 4d  with d = o - z (o = 0 past the last real row)
+template <class K, int N0>
+__device__ __forceinline__ void load_nodes(const K* __restrict__ base, uint32_t col, uint64_t h, uint64_t i, K (&v)[3]) {
+    using O = Ops<K>;
+    const K* c = base + (uint64_t)col * h;
+    const K z = O::load(c, 2 * i);
+    const K o = (2 * i + 1 < h) ? O::load(c, 2 * i + 1) : O::zero();
+    const K d = O::sub(o, z);
+    const K d2 = O::add(d, d);
+    if (N0 == 0) v[0] = z;
+    v[1] = O::add(z, d2);
+    v[2] = O::add(v[1], d2);
+}
 
 // partial[(blockIdx.x * 3 + node) * 3 + {0,1,2}] =
 //   0: sum_rows E[i] * [constraints](node)     1 (node 0 only): sum_rows E[i] * sum_j g_j col_j(0)     2 (node 0 only): same at 1
-template <class K, bool SMEM>
+// FIRST (round 0): the constraints vanish on the boolean rows, so node 0 is skipped (N0 = 1).
+template <class K, bool SMEM, bool FIRST>
 __global__ void __launch_bounds__(ZC_BLOCK) zc_sum_kernel(const ZcJob* __restrict__ jobs, int n_jobs, const ChipProg* __restrict__ chips,
                                                           const uint32_t* __restrict__ pv, const uint32_t* __restrict__ gkr_pows,
-                                                          const uint32_t* __restrict__ E, int first_round, uint32_t* __restrict__ partial) {
+                                                          const uint32_t* __restrict__ E, uint32_t* __restrict__ partial) {
     using O = Ops<K>;
+    constexpr int N0 = FIRST ? 1 : 0;
     extern __shared__ __align__(16) unsigned char zc_smem[];
-    __shared__ uint32_t red[3][4][ZC_BLOCK / 32];
+    __shared__ uint32_t red[5][4][ZC_BLOCK / 32];
     const ZcJob job = jobs[find_job(jobs, n_jobs, blockIdx.x)];
     const ChipProg& prog = chips[job.chip];
     const K* main = static_cast<const K*>(job.main);
     const K* prep = static_cast<const K*>(job.prep);
     const uint64_t h = job.h;
-    const int node = blockIdx.y;  // 0,1,2 <-> t = 0,2,4
     const uint64_t terms = (h + 1) / 2;
     RegFile<K, SMEM> rf(zc_smem);
-    Ext acc_c = kb::ext_zero(), acc_a = kb::ext_zero(), acc_b = kb::ext_zero();
-    const bool run_constraints = !(first_round && node == 0);
+    Ext acc[5];  // constraints at nodes 0,1,2 ; opening-batching term at 0 and at 1
+#pragma unroll
+    for (int a = 0; a < 5; a++) acc[a] = kb::ext_zero();
     const ZcInstr* __restrict__ zc = prog.zc;
     const uint32_t n_zc = prog.n_zc;
     for (uint64_t i = (uint64_t)(blockIdx.x - job.blk_start) * ZC_BLOCK + threadIdx.x; i < terms; i += (uint64_t)job.nblk * ZC_BLOCK) {
         const Ext e = kb::ext_load(E + 4 * i);
-        if (run_constraints) {
-            Ext row = kb::ext_zero();
-            ZcInstr in = n_zc ? zc[0] : ZcInstr{};
-            for (uint32_t pc = 0; pc < n_zc; pc++) {
-                const ZcInstr nxt = zc[pc + 1 < n_zc ? pc + 1 : pc];  // prefetch: the stream is block-uniform and L1 resident
-                switch (in.op) {
-                    case ZC_LOAD_MAIN: rf.set(in.out, interp_pair<K>(main, (uint32_t)in.a | ((uint32_t)in.b << 16), h, i, node)); break;
-                    case ZC_LOAD_PREP: rf.set(in.out, interp_pair<K>(prep, (uint32_t)in.a | ((uint32_t)in.b << 16), h, i, node)); break;
-                    case ZC_CONST: rf.set(in.out, O::from_base(prog.consts[in.a])); break;
-                    case ZC_PUBLIC: rf.set(in.out, O::from_base(pv[prog.publics[in.a]])); break;
-                    case ZC_ADD: { const K x = rf.get(in.a), y = rf.get(in.b); rf.set(in.out, O::add(x, y)); break; }
-                    case ZC_SUB: { const K x = rf.get(in.a), y = rf.get(in.b); rf.set(in.out, O::sub(x, y)); break; }
-                    case ZC_MUL: { const K x = rf.get(in.a), y = rf.get(in.b); rf.set(in.out, O::mul(x, y)); break; }
-                    case ZC_NEG: { const K x = rf.get(in.a); rf.set(in.out, O::sub(O::zero(), x)); break; }
-                    case ZC_ASSERT: row = kb::ext_add(row, O::scale(kb::ext_load(job.alpha_pows + 4 * in.b), rf.get(in.a))); break;
-                    default: __trap();
+        Ext row[3] = {kb::ext_zero(), kb::ext_zero(), kb::ext_zero()};
+        ZcInstr in = n_zc ? zc[0] : ZcInstr{};
+        for (uint32_t pc = 0; pc < n_zc; pc++) {
+            const ZcInstr nxt = zc[pc + 1 < n_zc ? pc + 1 : pc];  // prefetch: the stream is block-uniform and L1 resident
+            switch (in.op) {
+                case ZC_LOAD_MAIN: case ZC_LOAD_PREP: {
+                    K v[3];
+                    load_nodes<K, N0>(in.op == ZC_LOAD_MAIN ? main : prep, (uint32_t)in.a | ((uint32_t)in.b << 16), h, i, v);
+#pragma unroll
+                    for (int n = N0; n < 3; n++) rf.set(in.out, n, v[n]);
+                    break;
                 }
-                in = nxt;
+                case ZC_CONST: { const K c = O::from_base(prog.consts[in.a]);
+#pragma unroll
+                    for (int n = N0; n < 3; n++) rf.set(in.out, n, c);
+                    break; }
+                case ZC_PUBLIC: { const K c = O::from_base(pv[prog.publics[in.a]]);
+#pragma unroll
+                    for (int n = N0; n < 3; n++) rf.set(in.out, n, c);
+                    break; }
+                case ZC_ADD: {
+                    K r[3];
+#pragma unroll
+                    for (int n = N0; n < 3; n++) r[n] = O::add(rf.get(in.a, n), rf.get(in.b, n));
+#pragma unroll
+                    for (int n = N0; n < 3; n++) rf.set(in.out, n, r[n]);
+                    break; }
+                case ZC_SUB: {
+                    K r[3];
+#pragma unroll
+                    for (int n = N0; n < 3; n++) r[n] = O::sub(rf.get(in.a, n), rf.get(in.b, n));
+#pragma unroll
+                    for (int n = N0; n < 3; n++) rf.set(in.out, n, r[n]);
+                    break; }
+                case ZC_MUL: {
+                    K r[3];
+#pragma unroll
+                    for (int n = N0; n < 3; n++) r[n] = O::mul(rf.get(in.a, n), rf.get(in.b, n));
+#pragma unroll
+                    for (int n = N0; n < 3; n++) rf.set(in.out, n, r[n]);
+                    break; }
+                case ZC_NEG: {
+                    K r[3];
+#pragma unroll
+                    for (int n = N0; n < 3; n++) r[n] = O::sub(O::zero(), rf.get(in.a, n));
+#pragma unroll
+                    for (int n = N0; n < 3; n++) rf.set(in.out, n, r[n]);
+                    break; }
+                case ZC_ASSERT: {
+                    const Ext al = kb::ext_load(job.alpha_pows + 4 * in.b);
+#pragma unroll
+                    for (int n = N0; n < 3; n++) row[n] = kb::ext_add(row[n], O::scale(al, rf.get(in.a, n)));
+                    break; }
+                default: __trap();
             }
-            acc_c = kb::ext_add(acc_c, kb::ext_mul(row, e));
+            in = nxt;
         }
-        if (node == 0) {
-            // the opening-batching term is linear in the row variable: evaluate it at 0 and 1 only
-            Ext s0 = kb::ext_zero(), s1 = kb::ext_zero();
-            const bool has_o = 2 * i + 1 < h;
-            for (uint32_t j = 0; j < prog.main_w; j++) {
-                const Ext g = kb::ext_load(gkr_pows + 4 * j);
-                const K* c = main + (uint64_t)j * h;
-                s0 = kb::ext_add(s0, O::scale(g, O::load(c, 2 * i)));
-                if (has_o) s1 = kb::ext_add(s1, O::scale(g, O::load(c, 2 * i + 1)));
-            }
-            for (uint32_t j = 0; j < prog.prep_w; j++) {
-                const Ext g = kb::ext_load(gkr_pows + 4 * (prog.main_w + j));
-                const K* c = prep + (uint64_t)j * h;
-                s0 = kb::ext_add(s0, O::scale(g, O::load(c, 2 * i)));
-                if (has_o) s1 = kb::ext_add(s1, O::scale(g, O::load(c, 2 * i + 1)));
-            }
-            acc_a = kb::ext_add(acc_a, kb::ext_mul(s0, e));
-            acc_b = kb::ext_add(acc_b, kb::ext_mul(s1, e));
+#pragma unroll
+        for (int n = N0; n < 3; n++) acc[n] = kb::ext_add(acc[n], kb::ext_mul(row[n], e));
+        // the opening-batching term is linear in the row variable: evaluate it at 0 and 1 only
+        Ext s0 = kb::ext_zero(), s1 = kb::ext_zero();
+        const bool has_o = 2 * i + 1 < h;
+        for (uint32_t j = 0; j < prog.main_w; j++) {
+            const Ext g = kb::ext_load(gkr_pows + 4 * j);
+            const K* c = main + (uint64_t)j * h;
+            s0 = kb::ext_add(s0, O::scale(g, O::load(c, 2 * i)));
+            if (has_o) s1 = kb::ext_add(s1, O::scale(g, O::load(c, 2 * i + 1)));
         }
+        for (uint32_t j = 0; j < prog.prep_w; j++) {
+            const Ext g = kb::ext_load(gkr_pows + 4 * (prog.main_w + j));
+            const K* c = prep + (uint64_t)j * h;
+            s0 = kb::ext_add(s0, O::scale(g, O::load(c, 2 * i)));
+            if (has_o) s1 = kb::ext_add(s1, O::scale(g, O::load(c, 2 * i + 1)));
+        }
+        acc[3] = kb::ext_add(acc[3], kb::ext_mul(s0, e));
+        acc[4] = kb::ext_add(acc[4], kb::ext_mul(s1, e));
     }
-    // block reduction: warp shuffles, then one warp over the per-warp sums
+    // block reduction: warp shuffles, then one thread per word over the per-warp sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Ext* accs[3] = {&acc_c, &acc_a, &acc_b};
-    const int n_acc = node == 0 ? 3 : 1;
-    for (int a = 0; a < n_acc; a++)
+#pragma unroll
+    for (int a = 0; a < 5; a++)
+#pragma unroll
         for (int l = 0; l < 4; l++) {
-            uint32_t v = accs[a]->c[l];
+            uint32_t v = acc[a].c[l];
             for (int s = 16; s > 0; s >>= 1) v = kb::add(v, __shfl_down_sync(0xffffffffu, v, s));
             if (lane == 0) red[a][l][warp] = v;
         }
     __syncthreads();
-    if (threadIdx.x < 12) {
-        const int a = threadIdx.x >> 2, l = threadIdx.x & 3;
+    if (threadIdx.x < 36) {
+        // word w of the block's 36: node = w / 12, slot = (w / 4) % 3, limb = w % 4
+        const int node = threadIdx.x / 12, slot = (threadIdx.x >> 2) % 3, l = threadIdx.x & 3;
+        const int a = slot == 0 ? node : (node == 0 ? 2 + slot : -1);
         uint32_t v = 0;
-        if (a < n_acc)
+        if (a >= 0)
             for (int w = 0; w < ZC_BLOCK / 32; w++) v = kb::add(v, red[a][l][w]);
-        partial[((uint64_t)(blockIdx.x * 3 + node) * 3 + a) * 4 + l] = v;
+        partial[(uint64_t)blockIdx.x * 36 + threadIdx.x] = v;
     }
 }
 
@@ -373,6 +416,8 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     HostChallenger ch;
     SP1_TRY(ch.init(ctx, h_chal));
     PhaseTimer t_all(ctx, "zerocheck.total");
+    HostAccum acc_wait(ctx, "zerocheck.host_wait"), acc_math(ctx, "zerocheck.host_math"), acc_setup(ctx, "zerocheck.host_setup");
+    auto t_setup = std::make_unique<HostSpan>(acc_setup);
     const E4 alpha = E4::load(h_alpha), gamma = E4::load(h_gamma);
 
     struct St {
@@ -438,7 +483,7 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
 
     // ---- the whole launch plan is known up front (heights halve deterministically): job tables of every round, one upload ----
     // tiers of the shared-memory register file (registers per thread); chips above the last tier use the local-memory kernel
-    static const uint32_t TIER_REGS[3] = {16, 48, 96};
+    static const uint32_t TIER_REGS[3] = {8, 16, 32};  // x 3 nodes x 16 B x 128 threads = 48 / 96 / 192 KiB per block (EF rounds)
     auto tier_of = [&](uint32_t regs) { for (int t = 0; t < 3; t++) if (regs <= TIER_REGS[t]) return t; return 3; };
     struct Launch { size_t job0; uint32_t n_jobs, blocks, regs; int tier; };
     struct RoundPlan { std::vector<Launch> sums; size_t fix0; uint32_t fix_jobs, fix_blocks; std::vector<uint32_t> chip_of_job; size_t job0; };
@@ -502,18 +547,18 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     if ((size_t)max_jobs * 36 > SP1_MAIL_WORDS) return sp1b200_set_error("zerocheck: %u chips exceed the mailbox payload", max_jobs);
     d_sums = sp1b200_mail_dev(ctx);
     SP1_CUDA(cudaMemsetAsync(d_final, 0, (wsum ? wsum : 1) * 16, st));
-    auto launch_sum = [&](const Launch& Lc, bool ext, int first, uint32_t* part) -> sp1b200_err {
-        dim3 g(Lc.blocks, 3, 1);
+    auto launch_sum = [&](const Launch& Lc, bool ext, uint32_t* part) -> sp1b200_err {
         auto go = [&](auto kern, size_t smem) -> sp1b200_err {
             if (smem > 48 * 1024) SP1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SP1_LAUNCH(ctx, kern, g, ZC_BLOCK, smem, d_jobs + Lc.job0, (int)Lc.n_jobs, m->d_chips, d_pv, d_gw, d_E[ecur], first, part);
+            SP1_LAUNCH(ctx, kern, Lc.blocks, ZC_BLOCK, smem, d_jobs + Lc.job0, (int)Lc.n_jobs, m->d_chips, d_pv, d_gw, d_E[ecur], part);
             return nullptr;
         };
-        if (Lc.tier == 3) return ext ? go(zc_sum_kernel<Ext, false>, 0) : go(zc_sum_kernel<uint32_t, false>, 0);
-        const size_t regs = Lc.regs;  // the file is sized by the launch's worst chip
-        return ext ? go(zc_sum_kernel<Ext, true>, regs * ZC_BLOCK * 16) : go(zc_sum_kernel<uint32_t, true>, regs * ZC_BLOCK * 4);
+        if (Lc.tier == 3) return ext ? go(zc_sum_kernel<Ext, false, false>, 0) : go(zc_sum_kernel<uint32_t, false, true>, 0);
+        const size_t regs = Lc.regs;  // the file is sized by the launch's worst chip: regs x 3 nodes x block
+        return ext ? go(zc_sum_kernel<Ext, true, false>, regs * 3 * ZC_BLOCK * 16) : go(zc_sum_kernel<uint32_t, true, true>, regs * 3 * ZC_BLOCK * 4);
     };
 
+    t_setup.reset();
     E4 lambda; ch.sample_ext(lambda.c);
     std::vector<E4> round_claims(nchips);
     E4 claimed_sum;
@@ -521,7 +566,7 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     std::vector<uint32_t> words;
     words.push_back(mlr);
     std::vector<E4> point;
-    std::vector<std::vector<E4>> unis(nchips);
+    std::vector<E4> ys((size_t)nchips * 4);  // per chip: round polynomial values at the nodes 0, 1, 2, 4
     std::vector<uint32_t> hs((size_t)max_jobs * 36);
     std::vector<int32_t> job_of_chip(nchips);
     const E4 two = E4::from_base(hf::to_monty(2)), four = E4::from_base(hf::to_monty(4)), three = E4::from_base(hf::to_monty(3));
@@ -531,23 +576,33 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
         {
             uint32_t blk = 0, seq = 0; size_t jb = 0;
             for (const Launch& Lc : R.sums) {
-                SP1_TRY(launch_sum(Lc, rd > 0, rd == 0, d_partial + (size_t)blk * 36));
+                SP1_TRY(launch_sum(Lc, rd > 0, d_partial + (size_t)blk * 36));
                 const Mail mail = sp1b200_mail_next(ctx); seq = mail.seq;
                 SP1_LAUNCH(ctx, zc_reduce_kernel, Lc.n_jobs, 128, 0, d_jobs + Lc.job0, d_partial + (size_t)blk * 36, d_sums + jb * 36, mail);
                 blk += Lc.blocks; jb += Lc.n_jobs;
             }
             if (jb) {  // launches complete in stream order: the last sequence number covers every tier
+                HostSpan sp(acc_wait);
                 SP1_TRY(sp1b200_mail_wait(ctx, seq));
                 memcpy(hs.data(), sp1b200_mail_host(ctx), jb * 36 * 4);
             }
         }
+        HostSpan sp_math(acc_math);
         std::fill(job_of_chip.begin(), job_of_chip.end(), -1);
         for (size_t j = 0; j < R.chip_of_job.size(); j++) job_of_chip[R.chip_of_job[j]] = (int32_t)j;
-        std::vector<E4> rlc(1);
+        // Every chip's round polynomial goes through the same five nodes {0, 1, 2, 4, b} (b depends only on the shared point),
+        // and interpolation is linear: combine the chips' node values with the lambda powers first, interpolate ONCE.
+        const E4 last = gp[mlr - 1 - rd];
+        const E4 bnode = (E4::one() - last) * hf::inv(E4::one() - (last + last));
+        const E4 nodes[5] = {E4(), E4::one(), two, four, bnode};
+        E4 basis[5][5];
+        hf::lagrange_basis<5>(nodes, basis);
+        const E4 f0 = E4::one() - last, f2 = last * hf::to_monty(3) - E4::one(), f4 = last * hf::to_monty(7) - three;
+        E4 Y[4];  // lambda-combined values at nodes 0, 1, 2, 4 (the value at b is zero by construction)
         for (size_t k = 0; k < nchips; k++) {
             St& s = S[k];
-            std::vector<E4>& u = unis[k];
-            if (s.h == 0) { u.assign(5, E4()); }
+            E4* y = &ys[4 * k];
+            if (s.h == 0) { y[0] = y[1] = y[2] = y[3] = E4(); }
             else {
                 // sums: [node][slot] ; y_t = C_t + A + t (B - A) with A, B the opening-batching term at 0 and 1
                 const uint32_t* q = &hs[(size_t)job_of_chip[k] * 36];
@@ -564,25 +619,19 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
                     eth = E4::one();
                     for (size_t t = 0; t < kk; t++) eth = eth * (((th >> (kk - 1 - t)) & 1) ? s.zeta[t] : E4::one() - s.zeta[t]);
                 }
-                const E4 last = s.zeta.back();
                 const E4 msb = s.eq_adj * eth;
                 const E4 v0 = s.vg.fix_last(E4()).at(th), v2 = s.vg.fix_last(two).at(th), v4 = s.vg.fix_last(four).at(th);
-                const E4 f0 = E4::one() - last;
                 y0 = y0 * (f0 * s.eq_adj) - s.pra * v0 * msb * f0;
-                const E4 y1 = round_claims[k] - y0;
-                const E4 f2 = last * hf::to_monty(3) - E4::one();
                 y2 = y2 * (f2 * s.eq_adj) - s.pra * v2 * msb * f2;
-                const E4 f4 = last * hf::to_monty(7) - E4::from_base(hf::to_monty(3));
                 y4 = y4 * (f4 * s.eq_adj) - s.pra * v4 * msb * f4;
-                const E4 bnode = (E4::one() - last) * hf::inv(E4::one() - (last + last));
-                u = host_interpolate({E4(), E4::one(), two, four, bnode}, {y0, y1, y2, y4, E4()});
+                y[0] = y0; y[1] = round_claims[k] - y0; y[2] = y2; y[3] = y4;
             }
-            std::vector<E4> nr(std::max(rlc.size(), u.size()));
-            for (size_t i = 0; i < nr.size(); i++) nr[i] = (i < rlc.size() ? rlc[i] * lambda : E4()) + (i < u.size() ? u[i] : E4());
-            rlc.swap(nr);
+            for (int i = 0; i < 4; i++) Y[i] = (k ? Y[i] * lambda : E4()) + y[i];
         }
+        E4 rlc[5];
+        for (int c5 = 0; c5 < 5; c5++) for (int i = 0; i < 4; i++) rlc[c5] = rlc[c5] + basis[i][c5] * Y[i];
         for (auto& c : rlc) ch.observe_n(c.c, 4);
-        words.push_back((uint32_t)rlc.size());
+        words.push_back(5);
         for (auto& c : rlc) words.insert(words.end(), c.c, c.c + 4);
         E4 a; ch.sample_ext(a.c);
         point.insert(point.begin(), a);
@@ -591,12 +640,14 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
             if (rd == 0) SP1_LAUNCH(ctx, zc_fix_kernel<uint32_t>, R.fix_blocks, 256, 0, d_fjobs + R.fix0, (int)R.fix_jobs, da);
             else SP1_LAUNCH(ctx, zc_fix_kernel<Ext>, R.fix_blocks, 256, 0, d_fjobs + R.fix0, (int)R.fix_jobs, da);
         }
+        E4 La[4];  // L_i(a) for the four non-zero nodes
+        for (int i = 0; i < 4; i++) La[i] = hf::eval_poly<5>(basis[i], a);
         for (size_t k = 0; k < nchips; k++) {
             St& s = S[k];
-            round_claims[k] = host_eval_poly(unis[k], a);
+            const E4* y = &ys[4 * k];
+            round_claims[k] = y[0] * La[0] + y[1] * La[1] + y[2] * La[2] + y[3] * La[3];
             s.vg = s.vg.fix_last(a);
             if (s.h == 0) continue;
-            const E4 last = s.zeta.back();
             s.eq_adj = s.eq_adj * (a * last + (E4::one() - a) * (E4::one() - last));
             s.zeta.pop_back();
             s.h = (s.h + 1) / 2;

@@ -1,0 +1,148 @@
+// Poseidon2-KoalaBear permutation variants on B200 (development aid, not part of the product): Gperm/s with the state in
+// registers, every variant cross-checked bit-for-bit against p2::permute (the product code, itself checked against the oracle).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 --expt-relaxed-constexpr -I../sp1_b200/csrc -o p2_bench p2_bench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "poseidon2.cuh"
+
+namespace v {
+using kb::P;
+constexpr uint32_t MP = 0x7effffffu;  // -p^-1
+constexpr uint32_t MU = 0x81000001u;  // +p^-1
+
+__device__ __forceinline__ uint64_t mulw(uint32_t a, uint32_t b) { uint64_t r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint64_t madw(uint32_t a, uint32_t b, uint64_t c) { uint64_t r; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r; }
+
+// additive wide form: result in [0, 2p) for a*b < 2^32 p
+__device__ __forceinline__ uint32_t mont_wide_lazy(uint32_t a, uint32_t b) {
+    uint64_t t = mulw(a, b);
+    uint32_t m = (uint32_t)t * MP;
+    return (uint32_t)(madw(m, P, t) >> 32);
+}
+// x^3, wide form.  x = s + rc canonical; x2 lazy < 2p; x2 * x < 2 p^2 < 2^32 p
+__device__ __forceinline__ uint32_t sbox_wide(uint32_t s, uint32_t rc) {
+    uint32_t x = kb::add(s, rc);
+    uint32_t x2 = mont_wide_lazy(x, x);
+    uint32_t r = mont_wide_lazy(x2, x);
+    return kb::umin(r, r - P);
+}
+// mixed: first product by halves (sub form, lazy), second wide
+__device__ __forceinline__ uint32_t sbox_mixed(uint32_t s, uint32_t rc) {
+    uint32_t x = kb::add(s, rc);
+    uint32_t x2 = p2::mont_lazy(x, x);
+    uint32_t r = mont_wide_lazy(x2, x);
+    return kb::umin(r, r - P);
+}
+
+template <int SB> __device__ __forceinline__ uint32_t sbox(uint32_t s, uint32_t rc) {
+    if (SB == 0) return p2::sbox(s, rc);
+    if (SB == 1) return sbox_wide(s, rc);
+    return sbox_mixed(s, rc);
+}
+
+template <int SB, bool UNROLL>
+__device__ __forceinline__ void permute(uint32_t (&s)[16]) {
+    p2::ext_layer(s);
+    if (UNROLL) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) s[i] = sbox<SB>(s[i], p2::RC.ext[r * 16 + i]);
+            p2::ext_layer(s);
+        }
+#pragma unroll
+        for (int r = 0; r < 20; r++) { s[0] = sbox<SB>(s[0], p2::RC.inr[r]); p2::int_layer_lazy(s); }
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) s[i] = sbox<SB>(s[i], p2::RC.ext[r * 16 + i]);
+            p2::ext_layer(s);
+        }
+#pragma unroll 1
+        for (int r = 0; r < 20; r++) { s[0] = sbox<SB>(s[0], p2::RC.inr[r]); p2::int_layer_lazy(s); }
+    }
+#pragma unroll
+    for (int i = 1; i < 16; i++) { uint32_t x = s[i]; x = kb::umin(x, x - P); s[i] = kb::umin(x, x - P); }
+    if (UNROLL) {
+#pragma unroll
+        for (int r = 4; r < 8; r++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) s[i] = sbox<SB>(s[i], p2::RC.ext[r * 16 + i]);
+            p2::ext_layer(s);
+        }
+    } else {
+#pragma unroll 1
+        for (int r = 4; r < 8; r++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) s[i] = sbox<SB>(s[i], p2::RC.ext[r * 16 + i]);
+            p2::ext_layer(s);
+        }
+    }
+}
+}  // namespace v
+
+template <int V> struct Var;
+template <> struct Var<0> { static constexpr const char* name = "p2::permute (product)"; static __device__ void f(uint32_t (&s)[16]) { p2::permute(s); } };
+template <> struct Var<1> { static constexpr const char* name = "half-product sbox, loops"; static __device__ void f(uint32_t (&s)[16]) { v::permute<0, false>(s); } };
+template <> struct Var<2> { static constexpr const char* name = "wide sbox, loops"; static __device__ void f(uint32_t (&s)[16]) { v::permute<1, false>(s); } };
+template <> struct Var<3> { static constexpr const char* name = "mixed sbox, loops"; static __device__ void f(uint32_t (&s)[16]) { v::permute<2, false>(s); } };
+template <> struct Var<4> { static constexpr const char* name = "half-product sbox, fully unrolled"; static __device__ void f(uint32_t (&s)[16]) { v::permute<0, true>(s); } };
+template <> struct Var<5> { static constexpr const char* name = "wide sbox, fully unrolled"; static __device__ void f(uint32_t (&s)[16]) { v::permute<1, true>(s); } };
+
+template <int V>
+__global__ void __launch_bounds__(256) bench(uint32_t* out, int iters) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = (t * 2654435761u + i * 40503u) % kb::P;
+    for (int it = 0; it < iters; it++) Var<V>::f(s);
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) x ^= s[i];
+    out[t] = x;
+}
+template <int V>
+__global__ void check(uint32_t* bad) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a[16], b[16];
+    for (int i = 0; i < 16; i++) { a[i] = (t * 2246822519u + i * 3266489917u) % kb::P; if (t % 7 == 0 && i % 3 == 0) a[i] = kb::P - 1; if (t % 11 == 0) a[i] = 0; b[i] = a[i]; }
+    p2::permute(a);
+    Var<V>::f(b);
+    for (int i = 0; i < 16; i++) if (a[i] != b[i]) { atomicAdd(bad, 1); break; }
+}
+
+template <int V> void run(uint32_t* d_out, int sms) {
+    uint32_t* d_bad; cudaMalloc(&d_bad, 4); cudaMemset(d_bad, 0, 4);
+    check<V><<<64, 256>>>(d_bad);
+    uint32_t bad; cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost); cudaFree(d_bad);
+    const int iters = 64, blocks = sms * 8 * 4;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    bench<V><<<blocks, 256>>>(d_out, 2);
+    cudaDeviceSynchronize();
+    float best = 1e9;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        bench<V><<<blocks, 256>>>(d_out, iters);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, bench<V>);
+    double perms = (double)blocks * 256 * iters;
+    printf("%-40s %8.3f ms  %6.2f Gperm/s  regs=%d  mismatches=%u\n", Var<V>::name, best, perms / best * 1e-6, fa.numRegs, bad);
+}
+
+int main() {
+    cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
+    printf("%s, %d SMs\n", pr.name, pr.multiProcessorCount);
+    uint32_t* d_out; cudaMalloc(&d_out, (size_t)pr.multiProcessorCount * 32 * 256 * 4);
+    run<0>(d_out, pr.multiProcessorCount);
+    run<1>(d_out, pr.multiProcessorCount);
+    run<2>(d_out, pr.multiProcessorCount);
+    run<3>(d_out, pr.multiProcessorCount);
+    run<4>(d_out, pr.multiProcessorCount);
+    run<5>(d_out, pr.multiProcessorCount);
+    return 0;
+}

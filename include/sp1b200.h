@@ -58,6 +58,12 @@ sp1b200_err sp1b200_malloc(sp1b200_ctx* ctx, size_t bytes, void** d_out);
 sp1b200_err sp1b200_free(sp1b200_ctx* ctx, void* d_ptr);
 sp1b200_err sp1b200_memcpy_h2d(sp1b200_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 sp1b200_err sp1b200_memcpy_d2h(sp1b200_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* Double-buffered asynchronous upload (replaces the host->device trace transfer the reference does per shard in
+ * sp1-gpu/crates/jagged_tracegen: traces of shard k+1 are moved while shard k is proven).  Copies n_words words from
+ * (ideally pinned) host memory into library-owned slot 0 or 1 on a separate copy stream and returns the slot's device
+ * pointer; pass that pointer as main_dense_any to sp1b200_prove_shard / sp1b200_jagged_commit, which wait for the copy in
+ * stream order.  The slot is reused only after its previous consumer finished. */
+sp1b200_err sp1b200_upload_begin(sp1b200_ctx* ctx, const uint32_t* h_src, uint64_t n_words, int slot, uint32_t** d_out);
 /* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t sp1b200_launch_count(sp1b200_ctx* ctx);
 /* device time in ms of the most recent call of the named phase ("rs_encode", "leaf_hash", "compress", ...),

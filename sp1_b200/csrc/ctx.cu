@@ -88,6 +88,11 @@ sp1b200_err sp1b200_ctx_create(int device, const sp1b200_params* params, sp1b200
     SP1_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thresh = UINT64_MAX;
     SP1_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    SP1_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        SP1_CUDA(cudaEventCreateWithFlags(&c->slot_ready[i], cudaEventDisableTiming));
+        SP1_CUDA(cudaEventCreateWithFlags(&c->slot_free[i], cudaEventDisableTiming));
+    }
     SP1_CUDA(cudaHostAlloc((void**)&c->h_mail, (SP1_MAIL_HDR + SP1_MAIL_WORDS) * 4, cudaHostAllocMapped | cudaHostAllocPortable));
     memset(c->h_mail, 0, (SP1_MAIL_HDR + SP1_MAIL_WORDS) * 4);
     SP1_CUDA(cudaHostGetDevicePointer((void**)&c->d_mail, c->h_mail, 0));
@@ -107,6 +112,8 @@ void sp1b200_ctx_destroy(sp1b200_ctx* c) {
     cudaFree(c->d_TH); cudaFree(c->d_TL);
     cudaFree(c->d_mail_counter);
     if (c->h_mail) cudaFreeHost(c->h_mail);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int i = 0; i < 2; i++) { cudaFree(c->d_slot[i]); if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]); if (c->slot_free[i]) cudaEventDestroy(c->slot_free[i]); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -143,7 +150,45 @@ sp1b200_err sp1b200_mail_wait(sp1b200_ctx* c, uint32_t seq) {
     }
 }
 
-sp1b200_err sp1b200_ctx_sync(sp1b200_ctx* c) { SP1_CUDA(cudaStreamSynchronize(c->stream)); return nullptr; }
+// Start copying a shard's traces from (pinned) host memory into upload slot `slot` on the copy stream and return the slot's
+// device pointer.  The copy overlaps whatever the main stream is doing (normally the proof of the previous shard); a later
+// call on the main stream that consumes the pointer (sp1b200_prove_shard / sp1b200_jagged_commit) waits for it in stream
+// order, and the slot is not overwritten before its previous consumer has finished.
+sp1b200_err sp1b200_upload_begin(sp1b200_ctx* c, const uint32_t* h_src, uint64_t n_words, int slot, uint32_t** d_out) {
+    if (slot < 0 || slot > 1) return sp1b200_set_error("upload_begin: slot must be 0 or 1");
+    if (!h_src || !d_out) return sp1b200_set_error("upload_begin: NULL argument");
+    if (c->slot_words[slot] < n_words) {
+        SP1_CUDA(cudaStreamSynchronize(c->stream));
+        SP1_CUDA(cudaStreamSynchronize(c->copy_stream));
+        cudaFree(c->d_slot[slot]); c->d_slot[slot] = nullptr; c->slot_words[slot] = 0;
+        SP1_CUDA(cudaMalloc((void**)&c->d_slot[slot], (n_words ? n_words : 1) * 4));
+        c->slot_words[slot] = n_words;
+    }
+    SP1_CUDA(cudaStreamWaitEvent(c->copy_stream, c->slot_free[slot], 0));  // a never-recorded event is complete
+    SP1_CUDA(cudaMemcpyAsync(c->d_slot[slot], h_src, n_words * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    SP1_CUDA(cudaEventRecord(c->slot_ready[slot], c->copy_stream));
+    c->slot_pending[slot] = true;
+    *d_out = c->d_slot[slot];
+    return nullptr;
+}
+// stream-ordered wait for a pending upload if `d_ptr` is one of the slots; returns the slot index or -1
+int sp1b200_upload_acquire(sp1b200_ctx* c, const void* d_ptr) {
+    for (int i = 0; i < 2; i++)
+        if (d_ptr && d_ptr == c->d_slot[i]) {
+            if (c->slot_pending[i]) { cudaStreamWaitEvent(c->stream, c->slot_ready[i], 0); c->slot_pending[i] = false; }
+            return i;
+        }
+    return -1;
+}
+void sp1b200_upload_release(sp1b200_ctx* c, int slot) {
+    if (slot >= 0 && slot < 2) cudaEventRecord(c->slot_free[slot], c->stream);
+}
+
+sp1b200_err sp1b200_ctx_sync(sp1b200_ctx* c) {
+    SP1_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) SP1_CUDA(cudaStreamSynchronize(c->copy_stream));
+    return nullptr;
+}
 void* sp1b200_ctx_stream(sp1b200_ctx* c) { return (void*)c->stream; }
 uint64_t sp1b200_launch_count(sp1b200_ctx* c) { return c->launches; }
 float sp1b200_last_phase_ms(sp1b200_ctx* c, const char* phase) {

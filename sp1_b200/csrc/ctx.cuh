@@ -30,6 +30,13 @@ struct sp1b200_ctx {
     uint32_t* d_mail = nullptr;         // device alias of h_mail
     uint32_t* d_mail_counter = nullptr; // device memory: blocks finished in the current posting kernel
     uint32_t mail_seq = 0;
+    // double-buffered upload slots: host traces of the NEXT shard are copied on `copy_stream` while the current one is proven
+    cudaStream_t copy_stream = nullptr;
+    uint32_t* d_slot[2] = {nullptr, nullptr};
+    uint64_t slot_words[2] = {0, 0};
+    cudaEvent_t slot_ready[2] = {nullptr, nullptr};   // recorded on copy_stream after the upload
+    cudaEvent_t slot_free[2] = {nullptr, nullptr};    // recorded on stream when the consumer (prove_shard) is done with the slot
+    bool slot_pending[2] = {false, false};
 };
 constexpr size_t SP1_MAIL_HDR = 16;               // words before the payload (64-byte aligned payload)
 constexpr size_t SP1_MAIL_WORDS = 1 << 16;        // payload capacity in words (256 KiB)
@@ -130,3 +137,5 @@ struct DevBuf {
 };
 
 bool sp1b200_is_device_ptr(const void* p);
+extern "C" int sp1b200_upload_acquire(sp1b200_ctx* c, const void* d_ptr);
+extern "C" void sp1b200_upload_release(sp1b200_ctx* c, int slot);

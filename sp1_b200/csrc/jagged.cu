@@ -491,7 +491,9 @@ sp1b200_err sp1b200_jagged_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, u
     const uint64_t added = padded - area;
     r->area = area; r->padded_area = padded;
     SP1_CUDA(cudaMallocAsync((void**)&r->d_dense, padded * 4, ctx->stream));
+    const int up_slot = sp1b200_upload_acquire(ctx, dense_any);  // dense_any may be an upload slot still being filled
     if (area) SP1_CUDA(cudaMemcpyAsync(r->d_dense, dense_any, area * 4, cudaMemcpyDefault, ctx->stream));
+    sp1b200_upload_release(ctx, up_slot);                        // the slot is free once this copy has run
     if (added) SP1_CUDA(cudaMemsetAsync(r->d_dense + area, 0, added * 4, ctx->stream));
     sp1b200_err e = sp1b200_stacked_commit(ctx, r->d_dense, padded / S, keep_codeword, r->original_commit, &r->stacked);
     if (e) { cudaFreeAsync(r->d_dense, ctx->stream); return e; }

@@ -20,6 +20,7 @@
 sp1b200_err sp1b200_rs_encode_device(sp1b200_ctx*, const uint32_t*, uint64_t, uint32_t, uint32_t, uint32_t*);
 sp1b200_err sp1b200_merkle_commit_device(sp1b200_ctx*, const uint32_t*, uint64_t, uint32_t, uint32_t*, uint32_t*);
 sp1b200_err sp1b200_merkle_tree_from_leaves_device(sp1b200_ctx*, uint32_t*, uint32_t, uint32_t, uint32_t*);
+sp1b200_err sp1b200_fri_tree_device(sp1b200_ctx*, const uint32_t*, uint64_t, uint32_t*, uint32_t, uint32_t*, Mail);
 
 struct sp1b200_commit {
     uint64_t ncols = 0;
@@ -426,16 +427,18 @@ sp1b200_err sp1b200_stacked_prove(sp1b200_ctx* ctx, sp1b200_commit* const* round
         std::swap(cur_E, nxt_E);
         unsigned nblk = (unsigned)((n_cur / 2 + 255) / 256);
         if (nblk > 1024) nblk = 1024;
-        SP1_LAUNCH(ctx, dot_even_kernel, nblk, 256, 0, cur_E, cur_mle, n_cur / 2, d_part);
-        std::vector<uint32_t> parts(nblk * 4);
-        SP1_CUDA(cudaMemcpyAsync(parts.data(), d_part, nblk * 16, cudaMemcpyDeviceToHost, st));
-        // leaves + tree of the current codeword (independent of the host round trip)
+        // the round's two results travel through the mailbox: payload [0,16) root + commitment, [16, 16 + 4 nblk) dot partials
+        uint32_t* mail_dev = sp1b200_mail_dev(ctx);
+        SP1_LAUNCH(ctx, dot_even_kernel, nblk, 256, 0, cur_E, cur_mle, n_cur / 2, mail_dev + 16);
+        // leaves + tree of the current codeword: leaf hashing fused into the first subtree launch, <= 3 launches per tree
         const uint32_t log_leaves = log_h + b - r - 1;
-        SP1_LAUNCH(ctx, fri_leaf_hash_kernel, blocks_for(m_cur / 2), 256, 0, cw_ptr[r], m_cur, tree_ptr[r]);
-        SP1_TRY(sp1b200_merkle_tree_from_leaves_device(ctx, tree_ptr[r], log_leaves, 8, d_rc));
+        const Mail mail = sp1b200_mail_next(ctx);
+        SP1_TRY(sp1b200_fri_tree_device(ctx, cw_ptr[r], m_cur, tree_ptr[r], log_leaves, mail_dev, mail));
+        SP1_TRY(sp1b200_mail_wait(ctx, mail.seq));
+        const uint32_t* mh = sp1b200_mail_host(ctx);
         uint32_t rc[16];
-        SP1_CUDA(cudaMemcpyAsync(rc, d_rc, 64, cudaMemcpyDeviceToHost, st));
-        SP1_CUDA(cudaStreamSynchronize(st));
+        memcpy(rc, mh, 64);
+        std::vector<uint32_t> parts(mh + 16, mh + 16 + (size_t)nblk * 4);
         E4 zero_val;
         for (unsigned k = 0; k < nblk; k++) zero_val = zero_val + E4::load(&parts[4 * k]);
         E4 one_val = (claim - zero_val) * hf::inv(last) + zero_val;

@@ -54,7 +54,7 @@ def load():
 # every symbol include/sp1b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 ERR_FUNCS = [
     "sp1b200_ctx_create", "sp1b200_ctx_sync", "sp1b200_malloc", "sp1b200_free", "sp1b200_memcpy_h2d",
-    "sp1b200_memcpy_d2h", "sp1b200_poseidon2_permute", "sp1b200_rs_encode", "sp1b200_merkle_commit", "sp1b200_grind",
+    "sp1b200_memcpy_d2h", "sp1b200_upload_begin", "sp1b200_poseidon2_permute", "sp1b200_rs_encode", "sp1b200_merkle_commit", "sp1b200_grind",
     "sp1b200_stacked_commit", "sp1b200_stacked_prove", "sp1b200_jagged_commit", "sp1b200_jagged_column_claims",
     "sp1b200_jagged_prove", "sp1b200_machine_create", "sp1b200_zerocheck", "sp1b200_logup_gkr", "sp1b200_prove_shard",
 ]
@@ -253,6 +253,13 @@ class Lib:
         self._chk(self.L.sp1b200_prove_shard(self.ctx, machine, prep_round, _ptr(main_dense), H, NM, _ptr(pv), C.c_uint32(pv.size),
                                              _ptr(rw), _ptr(challenger_state), _ptr(out), C.c_uint64(cap_words), C.byref(nw)))
         return out[:nw.value].copy()
+
+    def upload_begin(self, host_array, slot):
+        """async H2D of a (pinned) host array into upload slot 0/1 -> device pointer (int) to pass as main_dense"""
+        d = C.c_void_p()
+        n = host_array.numel() if hasattr(host_array, "numel") else host_array.size
+        self._chk(self.L.sp1b200_upload_begin(self.ctx, _ptr(host_array), C.c_uint64(n), C.c_int(slot), C.byref(d)))
+        return d.value
 
     def grind(self, state34, bits):
         st = np.ascontiguousarray(state34, dtype=np.uint32).copy()

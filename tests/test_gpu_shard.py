@@ -49,3 +49,31 @@ def test_prove_shard_matches_oracle(spec, log_stack, mlr):
 def test_prove_shard_medium():
     spec = [(4096, 2, True), (1024 + 32, 3, False), (0, 1, False), (8192, 1, True), (2048, 4, False)]
     _run(spec, 12, 13, seed=99, nq=16, pow_bits=8, batch_bits=5, gkr_bits=6)
+
+
+def test_prove_shard_from_upload_slots_is_identical():
+    """the double-buffered async upload path (sp1b200_upload_begin) feeds the same proof as a plain host pointer"""
+    import torch
+    from sp1_b200 import Lib
+    rng = np.random.default_rng(4242)
+    spec = [(2048, 2, True), (512 + 32, 3, False), (4096, 1, False)]
+    blob, heights, mains, preps, pv = _synth_machine_gkr(rng, spec)
+    names = [f"Chip{i:02d}" for i in range(len(heights))]
+    lib = Lib(0, log_stacking_height=11, max_log_row_count=12, num_queries=8, pow_bits=4, batch_pow_bits=2, gkr_pow_bits=3)
+    mach = lib.machine_create(blob)
+    _, prep_round = lib.jagged_commit([p for p in preps if p is not None])
+    dense = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(m).reshape(-1) for m in mains if m.size]))
+    st0 = O.Challenger().st.copy()
+    ref = lib.prove_shard(mach, prep_round, dense, heights, names, pv, st0.copy())
+    pinned = torch.from_numpy(dense.view(np.int32)).pin_memory()
+    other = torch.from_numpy((dense ^ np.uint32(1)).view(np.int32)).pin_memory()   # a different shard in the other slot
+    d0 = lib.upload_begin(pinned, 0)
+    d1 = lib.upload_begin(other, 1)
+    a = lib.prove_shard(mach, prep_round, d0, heights, names, pv, st0.copy())
+    d0b = lib.upload_begin(pinned, 0)          # slot 0 reused while slot 1 is still pending
+    b = lib.prove_shard(mach, prep_round, d0b, heights, names, pv, st0.copy())
+    assert d0 == d0b and d1 != d0
+    assert (a == ref).all() and (b == ref).all()
+    lib.jagged_round_free(prep_round)
+    lib.machine_free(mach)
+    lib.close()

@@ -29,6 +29,7 @@ PHASES_DONE = ["commit(main): rs_encode + poseidon2 merkle", "logup-gkr: grind(1
                "zerocheck: constraint bytecode interpreter, 22 rounds over all chips",
                "jagged open: hadamard sumcheck + branching-program sumcheck",
                "stacked/basefold open: batch + 21 fold rounds + 2 grinds + 124 queries"]
+LEAF_TRAFFIC_BYTES_PER_LAUNCH = 3.193006e9 + 0.266801e9  # dram read + write of the S2 launch, profiles/ncu_big_kernels_r01_S2.txt
 PHASES_MISSING = []  # the step is the whole prove_shard_with_data body (shard.rs:650-792) on synthetic AIRs
 
 
@@ -189,7 +190,7 @@ def main():
     chal0 = HostChallenger().st.copy()
     padded_cells = ((cells + (1 << 21) - 1) >> 21) << 21
 
-    phase_names = ["commit.rs_encode", "commit.merkle", "shard.commit", "gkr.circuit", "gkr.rounds", "gkr.openings", "gkr.total", "gkr.host_wait", "gkr.host_interaction", "gkr.host_transcript",
+    phase_names = ["commit.rs_encode", "commit.merkle", "merkle.leaf_hash", "shard.commit", "gkr.circuit", "gkr.rounds", "gkr.openings", "gkr.total", "gkr.host_wait", "gkr.host_interaction", "gkr.host_transcript",
                    "zerocheck.total", "zerocheck.host_wait", "zerocheck.host_math", "zerocheck.host_setup", "jagged.little_poly", "jagged.sumcheck", "jagged.eval_sumcheck", "open.batch", "open.fri_rounds",
                    "open.queries", "open.total", "jagged.total", "shard.total"]
     acc = {}
@@ -255,6 +256,11 @@ def main():
     ntt_ms = phases.get("commit.rs_encode", float("nan"))
     ach = 20.0 * padded_cells / (ntt_ms / 1e3) / 1e9
     merkle_ms = phases.get("commit.merkle", float("nan"))
+    leaf_ms = phases.get("merkle.leaf_hash", float("nan"))
+    n_stacked = padded_cells >> 21
+    leaf_bytes = (4 * n_stacked + 32) * (1 << 23)
+    leaf_perms = (1 << 23) * ((n_stacked + 7) // 8)
+    leaf_gbs = leaf_bytes / (leaf_ms / 1e3) / 1e9
     perms = (1 << 23) * (((padded_cells >> 21) + 7) // 8) + (1 << 23)
     out = {
         "metric": "riscv_cycles_proven_per_second_core", "value": value, "unit": "cycles/s", "n_gpus": world, "steps": args.steps,
@@ -271,10 +277,21 @@ def main():
                         "the copy of step i+1 overlaps the proof of step i, every step's copy and proof read-back are inside the timed region"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "rs_encode (rs_step_a_fast<10> + rs_step_b_2048), all stacked columns of the main commit",
-                     "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
-                     "peak_source": peak_src,
-                     "note": "algorithmic 20 B/cell (4 B read + 16 B codeword write); measured with CUDA events on the library stream"},
+        "roofline": {"kernel": "leaf_hash_kernel (Poseidon2 sponge over the 2^23 codeword rows of the main commit; largest share of the step)",
+                     "bound": "hbm", "achieved": leaf_gbs, "peak": hbm, "unit": "GB/s", "frac": leaf_gbs / hbm,
+                     "traffic": LEAF_TRAFFIC_BYTES_PER_LAUNCH, "algorithmic_bytes_per_launch": leaf_bytes, "peak_source": peak_src,
+                     "limiter": "integer issue, not HBM: 12 Poseidon2 permutations per 412-byte row; the permutation costs ~63 SM-clocks "
+                                "per lane under the measured per-instruction issue rates (IMAD.HI 43/clk/SM dominates), "
+                                "i.e. ~4.4 Gperm/s per GPU at 1.9 GHz; see DESIGN.md section 3",
+                     "gperm_per_s": leaf_perms / (leaf_ms / 1e3) / 1e9, "issue_model_gperm_per_s": 4.43,
+                     "note": "algorithmic bytes = (4 B x stacked columns + 32 B digest) x 2^23 rows per launch; CUDA events on the library "
+                             "stream (phase merkle.leaf_hash); traffic = dram read+write of the same launch under ncu --set full (profiles/)"},
+        "roofline_rs_encode": {"kernel": "rs_encode (rs_step_a_fast<10> + rs_step_b_2048), all stacked columns of the main commit",
+                               "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                               "traffic": {"rs_step_a_fast<10>": 32.3e6, "rs_step_b_2048": 76.4e6, "per": "launch pair = 2 columns (cold cache under ncu)",
+                                           "algorithmic": 83.9e6},
+                               "peak_source": peak_src,
+                               "note": "algorithmic 20 B/cell (4 B read + 16 B codeword write); integer-pipe bound (46 modular products per cell), see DESIGN.md"},
         "kernels_ms_per_step": phases,
         "poseidon2": {"leaf+compress_perms_per_step": int(perms), "gperm_per_s": perms / (merkle_ms / 1e3) / 1e9,
                       "note": "INT32-ALU bound (see DESIGN.md), not HBM bound"},

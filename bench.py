@@ -4,8 +4,11 @@
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
   python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
 
-A "step" proves one synthetic shard (workload S2 by default: ~1.9e8 trace cells = 2^22 cycles at 45 cells/cycle):
-main-trace jagged commit (RS-encode NTT + Poseidon2 Merkle) followed by the phases listed in config.phases.
+A "step" proves one batch of `--inflight` synthetic shards per GPU (default 3, each on its own library context + CUDA stream +
+host transcript thread, so that the latency-bound sumcheck tails of one shard overlap the NTT / Poseidon2 kernels of another);
+a shard = workload S2 by default (~1.9e8 trace cells = 2^22 cycles at 45 cells/cycle): main-trace jagged commit (RS-encode NTT +
+Poseidon2 Merkle) followed by the phases listed in config.phases.  Per-phase times and the roofline lines are taken from a
+shard proven ALONE (kernels_ms_per_shard_alone).
 `value` is timed with the trace resident in HBM; `e2e` is the same step through the C ABI with the trace in pinned host
 memory (H2D inside the timed region, proof D2H).  Shards are independent: ranks never communicate in the data path
 (weak scaling); the only collectives are the barrier and the max-over-ranks of the elapsed time.
@@ -138,6 +141,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="S2", choices=list(W.WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3,
+                    help="shards proven concurrently per GPU (one library context + stream + host thread each): the latency-bound "
+                         "sumcheck tails of one shard overlap the NTT / Poseidon2 kernels of another")
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "serial"],
                     help="pipelined: H2D of step i+1 overlaps the proof of step i (upload slots); serial: plain host pointer per step")
     args = ap.parse_args()
@@ -187,6 +193,13 @@ def main():
     machine = lib.machine_create(mach["blob"])
     prep_rows = [h for h, _, wp in specs if wp]
     _, h_prep = lib.jagged_commit_dense(d_prep, prep_rows, [1] * len(prep_rows))
+    # further in-flight provers on the same GPU: own context (stream, mailbox, upload slots), own machine / preprocessed commit
+    provers = [(lib, machine, h_prep)]
+    for _ in range(1, args.inflight):
+        l2 = Lib(device=local)
+        m2 = l2.machine_create(mach["blob"])
+        _, p2 = l2.jagged_commit_dense(d_prep, prep_rows, [1] * len(prep_rows))
+        provers.append((l2, m2, p2))
     chal0 = HostChallenger().st.copy()
     padded_cells = ((cells + (1 << 21) - 1) >> 21) << 21
 
@@ -195,61 +208,85 @@ def main():
                    "open.queries", "open.total", "jagged.total", "shard.total"]
     acc = {}
 
-    def step(src, record=False):
+    def step(src, record=False, who=0):
+        l_, m_, p_ = provers[who]
         st = chal0.copy()
-        proof = lib.prove_shard(machine, h_prep, src, heights, names, pv, st)
-        if record:
+        proof = l_.prove_shard(m_, p_, src, heights, names, pv, st)
+        if record and who == 0:
             for n in phase_names:
-                v = lib.phase_ms(n)
+                v = l_.phase_ms(n)
                 if v >= 0:
                     acc[n] = acc.get(n, 0.0) + v
         return proof
 
-    def timed(src, k, pipelined_upload=False):
-        """k steps; pipelined_upload: src is the pinned host buffer, every step's H2D goes through the library's double-buffered
-        upload slots (C ABI sp1b200_upload_begin) so that the copy of step i+1 overlaps the proof of step i — all k copies are
-        inside the timed region."""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        lib.sync()
-        l0 = lib.launch_count()
-        e0.record(stream)
+    def run_steps(who, src, k, pipelined_upload, out):
+        l_ = provers[who][0]
         nbytes = 0
         if pipelined_upload:
-            nxt = lib.upload_begin(src, 0)
+            nxt = l_.upload_begin(src, 0)
             for i in range(k):
                 cur = nxt
                 if i + 1 < k:
-                    nxt = lib.upload_begin(src, (i + 1) & 1)
-                pr = step(cur, record=True)
-                nbytes = pr.nbytes
+                    nxt = l_.upload_begin(src, (i + 1) & 1)
+                nbytes = step(cur, record=True, who=who).nbytes
         else:
             for _ in range(k):
-                pr = step(src, record=True)
-                nbytes = pr.nbytes
-        e1.record(stream)
-        lib.sync()
+                nbytes = step(src, record=True, who=who).nbytes
+        out[who] = nbytes
+
+    def sync_all():
+        for l_, _, _ in provers:
+            l_.sync()
         torch.cuda.synchronize()
+
+    def timed(src, k, pipelined_upload=False):
+        """k steps, each step = one shard per in-flight prover; pipelined_upload: src is the pinned host buffer, every shard's H2D
+        goes through the library's double-buffered upload slots (C ABI sp1b200_upload_begin) so that the copy of the next shard
+        overlaps the proof of the current one — all copies are inside the timed region."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        sync_all()
+        l0 = sum(l_.launch_count() for l_, _, _ in provers)
+        e0.record(stream)
+        out = [0] * len(provers)
+        if len(provers) == 1:
+            run_steps(0, src, k, pipelined_upload, out)
+        else:
+            ths = [threading.Thread(target=run_steps, args=(w, src, k, pipelined_upload, out)) for w in range(len(provers))]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        sync_all()
+        e1.record(stream)
+        sync_all()
         if world > 1:
             dist.barrier()
         ms = SH.max_over_ranks(e0.elapsed_time(e1), dev)
-        return ms, lib.launch_count() - l0, nbytes
+        return ms, sum(l_.launch_count() for l_, _, _ in provers) - l0, out[0]
 
-    for _ in range(args.warmup):
-        step(d_main)
+    # warm-up in the same concurrent shape as the timed steps (the stream-ordered memory pool has to grow to its steady size)
+    if args.warmup:
+        timed(d_main, args.warmup)
+    acc.clear()
+    # per-phase / per-kernel times (roofline lines): ONE shard proven alone, outside the throughput measurement
+    PHASE_REPS = 2
+    for _ in range(PHASE_REPS):
+        step(d_main, record=True, who=0)
+    sync_all()
+    phases = {k: v / PHASE_REPS for k, v in acc.items()}
     acc.clear()
     with ClockSampler(local) as cs:
         ms_dev, launches, proof_bytes = timed(d_main, args.steps)
-        phases = {k: v / args.steps for k, v in acc.items()}
         acc.clear()
         if args.e2e_mode == "pipelined":
-            lib.upload_begin(h_main, 0); lib.upload_begin(h_main, 1); lib.sync()   # slot allocation is setup, not a step
+            for l_, _, _ in provers:
+                l_.upload_begin(h_main, 0); l_.upload_begin(h_main, 1); l_.sync()   # slot allocation is setup, not a step
         ms_e2e, _, _ = timed(h_main, args.steps, pipelined_upload=(args.e2e_mode == "pipelined"))
     clocks = cs.summary()
 
-    total_cycles = cycles * world  # every rank proves a shard of the same size (weak scaling)
+    total_cycles = cycles * world * len(provers)  # every rank proves `inflight` shards of the same size per step (weak scaling)
     value = total_cycles * args.steps / (ms_dev / 1e3)
     e2e = total_cycles * args.steps / (ms_e2e / 1e3)
     hbm, peak_src = peaks()
@@ -268,10 +305,10 @@ def main():
         "dtype": "u32 KoalaBear (Montgomery) / ext4", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {W.WORKLOADS[args.workload][1]}; main area {cells} cells = {cycles:.0f} cycles/shard "
                                f"(cells/45), {len(specs)} chips (synthetic AIR bytecode + LogUp interactions), {padded_cells >> 21} stacked columns of 2^21, blowup 4, "
-                               "124 queries, 16+5 PoW bits; one shard per GPU per step",
+                               f"124 queries, 16+5 PoW bits; {len(provers)} shard(s) in flight per GPU per step (one context + stream each)",
                    "phases": PHASES_DONE, "phases_not_yet_in_step": PHASES_MISSING,
                    "l2": "working set (>= 3 GB codeword per shard) exceeds the 126 MB L2 between iterations"},
-        "e2e": {"value": e2e, "unit": "cycles/s", "h2d_bytes_per_step": int(cells * 4), "d2h_bytes_per_step": int(proof_bytes),
+        "e2e": {"value": e2e, "unit": "cycles/s", "h2d_bytes_per_step": int(cells * 4) * len(provers), "d2h_bytes_per_step": int(proof_bytes) * len(provers),
                 "ms_per_step": ms_e2e / args.steps,
                 "note": "host trace in pinned memory -> sp1b200_upload_begin (two device slots, copy stream) -> sp1b200_prove_shard; "
                         "the copy of step i+1 overlaps the proof of step i, every step's copy and proof read-back are inside the timed region"},
@@ -292,7 +329,8 @@ def main():
                                            "algorithmic": 83.9e6},
                                "peak_source": peak_src,
                                "note": "algorithmic 20 B/cell (4 B read + 16 B codeword write); integer-pipe bound (46 modular products per cell), see DESIGN.md"},
-        "kernels_ms_per_step": phases,
+        "kernels_ms_per_shard_alone": phases,
+        "inflight": len(provers), "ms_per_shard": ms_dev / args.steps / len(provers),
         "poseidon2": {"leaf+compress_perms_per_step": int(perms), "gperm_per_s": perms / (merkle_ms / 1e3) / 1e9,
                       "note": "INT32-ALU bound (see DESIGN.md), not HBM bound"},
     }
@@ -303,9 +341,10 @@ def main():
             except Exception as e:  # the oracle is a checker; the GPU numbers stand without it
                 out["cpu_baseline"] = {"value": None, "unit": "cycles/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(out))
-    lib.jagged_round_free(h_prep)
-    lib.machine_free(machine)
-    lib.close()
+    for l_, m_, p_ in provers:
+        l_.jagged_round_free(p_)
+        l_.machine_free(m_)
+        l_.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -55,7 +55,7 @@ __global__ void grind_finalize_kernel(uint32_t* __restrict__ st, uint32_t w) {
 sp1b200_err sp1b200_grind_device(sp1b200_ctx* ctx, uint32_t* d_state, uint32_t bits, uint32_t* witness_canonical) {
     if (bits > 30) return sp1b200_set_error("grind: %u bits unsupported", bits);
     uint32_t* d_best;
-    SP1_CUDA(cudaMallocAsync((void**)&d_best, sizeof(uint32_t), ctx->stream));
+    SP1_CUDA(cudaMallocFromPoolAsync((void**)&d_best, sizeof(uint32_t), ctx->pool, ctx->stream));
     uint32_t batch = 1u << (bits + 2 < 16 ? 16 : (bits + 2 > 22 ? 22 : bits + 2));
     uint32_t best = 0xffffffffu;
     for (uint64_t base = 0; base < kb::P; base += batch) {
@@ -134,7 +134,7 @@ void HostChallenger::duplexing() {
 }
 sp1b200_err HostChallenger::init(sp1b200_ctx* c, const uint32_t* st34) {
     ctx = c;
-    SP1_CUDA(cudaMallocAsync((void**)&d_scratch, 34 * sizeof(uint32_t), c->stream));
+    SP1_CUDA(cudaMallocFromPoolAsync((void**)&d_scratch, 34 * sizeof(uint32_t), c->pool, c->stream));
     load(st34);
     return nullptr;
 }

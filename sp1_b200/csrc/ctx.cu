@@ -32,7 +32,7 @@ sp1b200_err DevBuf::in(sp1b200_ctx* c, const void* any, size_t nbytes) {
     ctx = c; bytes = nbytes;
     if (nbytes == 0) { d = nullptr; return nullptr; }
     if (sp1b200_is_device_ptr(any)) { d = const_cast<void*>(any); owned = false; return nullptr; }
-    SP1_CUDA(cudaMallocAsync(&d, nbytes, c->stream));
+    SP1_CUDA(cudaMallocFromPoolAsync(&d, nbytes, c->pool, c->stream));
     owned = true;
     SP1_CUDA(cudaMemcpyAsync(d, any, nbytes, cudaMemcpyHostToDevice, c->stream));
     return nullptr;
@@ -41,7 +41,7 @@ sp1b200_err DevBuf::out(sp1b200_ctx* c, void* any, size_t nbytes) {
     ctx = c; bytes = nbytes;
     if (nbytes == 0) { d = nullptr; return nullptr; }
     if (sp1b200_is_device_ptr(any)) { d = any; owned = false; return nullptr; }
-    SP1_CUDA(cudaMallocAsync(&d, nbytes, c->stream));
+    SP1_CUDA(cudaMallocFromPoolAsync(&d, nbytes, c->pool, c->stream));
     owned = true; host = any;
     return nullptr;
 }
@@ -83,11 +83,17 @@ sp1b200_err sp1b200_ctx_create(int device, const sp1b200_params* params, sp1b200
     SP1_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SP1_CUDA(cudaEventCreate(&c->ev0));
     SP1_CUDA(cudaEventCreate(&c->ev1));
-    // keep freed blocks in the stream-ordered pool instead of returning them to the driver
-    cudaMemPool_t pool;
-    SP1_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thresh = UINT64_MAX;
-    SP1_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    // a private stream-ordered pool per context; freed blocks stay in it instead of going back to the driver
+    {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        SP1_CUDA(cudaMemPoolCreate(&c->pool, &props));
+        uint64_t thresh = UINT64_MAX;
+        SP1_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    }
     SP1_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         SP1_CUDA(cudaEventCreateWithFlags(&c->slot_ready[i], cudaEventDisableTiming));
@@ -116,6 +122,7 @@ void sp1b200_ctx_destroy(sp1b200_ctx* c) {
     for (int i = 0; i < 2; i++) { cudaFree(c->d_slot[i]); if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]); if (c->slot_free[i]) cudaEventDestroy(c->slot_free[i]); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
+    if (c->pool) cudaMemPoolDestroy(c->pool);
     delete c;
 }
 
@@ -197,7 +204,7 @@ float sp1b200_last_phase_ms(sp1b200_ctx* c, const char* phase) {
 }
 
 sp1b200_err sp1b200_malloc(sp1b200_ctx* c, size_t bytes, void** d_out) {
-    SP1_CUDA(cudaMallocAsync(d_out, bytes, c->stream));
+    SP1_CUDA(cudaMallocFromPoolAsync(d_out, bytes, c->pool, c->stream));
     return nullptr;
 }
 sp1b200_err sp1b200_free(sp1b200_ctx* c, void* d_ptr) {
@@ -243,9 +250,9 @@ sp1b200_err sp1b200_merkle_commit(sp1b200_ctx* c, const uint32_t* mat_any, uint6
     SP1_TRY(in.in(c, mat_any, ((size_t)width << log_h) * sizeof(uint32_t)));
     uint32_t* layers = d_layers_out;
     size_t nd = ((size_t)2 << log_h) - 1;
-    if (!layers) SP1_CUDA(cudaMallocAsync((void**)&layers, nd * 8 * sizeof(uint32_t), c->stream));
+    if (!layers) SP1_CUDA(cudaMallocFromPoolAsync((void**)&layers, nd * 8 * sizeof(uint32_t), c->pool, c->stream));
     uint32_t* d_rc;
-    SP1_CUDA(cudaMallocAsync((void**)&d_rc, 16 * sizeof(uint32_t), c->stream));
+    SP1_CUDA(cudaMallocFromPoolAsync((void**)&d_rc, 16 * sizeof(uint32_t), c->pool, c->stream));
     PhaseTimer t(c, "merkle_commit");
     sp1b200_err e = sp1b200_merkle_commit_device(c, (const uint32_t*)in.d, width, log_h, layers, d_rc);
     t.stop();

@@ -16,6 +16,7 @@ struct sp1b200_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;  // this context's own stream-ordered pool: contexts proving concurrently never wait on each other's frees
     sp1b200_params params{};
     // TH[i] = w^(i * 2^12), TL[j] = w^j  with w = two-adic generator of order 2^24 (Montgomery words)
     uint32_t* d_TH = nullptr;

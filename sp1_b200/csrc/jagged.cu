@@ -55,7 +55,7 @@ struct DevFree {
     explicit DevFree(sp1b200_ctx* c) : ctx(c) {}
     ~DevFree() { for (void* p : ptrs) cudaFreeAsync(p, ctx->stream); }
     sp1b200_err alloc(void** p, size_t bytes) {
-        SP1_CUDA(cudaMallocAsync(p, bytes ? bytes : 4, ctx->stream));
+        SP1_CUDA(cudaMallocFromPoolAsync(p, bytes ? bytes : 4, ctx->pool, ctx->stream));
         ptrs.push_back(*p);
         return nullptr;
     }
@@ -490,7 +490,7 @@ sp1b200_err sp1b200_jagged_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, u
     const uint64_t padded = std::max(((area + S - 1) / S) * S, S);
     const uint64_t added = padded - area;
     r->area = area; r->padded_area = padded;
-    SP1_CUDA(cudaMallocAsync((void**)&r->d_dense, padded * 4, ctx->stream));
+    SP1_CUDA(cudaMallocFromPoolAsync((void**)&r->d_dense, padded * 4, ctx->pool, ctx->stream));
     const int up_slot = sp1b200_upload_acquire(ctx, dense_any);  // dense_any may be an upload slot still being filled
     if (area) SP1_CUDA(cudaMemcpyAsync(r->d_dense, dense_any, area * 4, cudaMemcpyDefault, ctx->stream));
     sp1b200_upload_release(ctx, up_slot);                        // the slot is free once this copy has run

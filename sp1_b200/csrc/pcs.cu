@@ -243,7 +243,7 @@ struct DevFree {
     explicit DevFree(sp1b200_ctx* c) : ctx(c) {}
     ~DevFree() { for (void* p : ptrs) cudaFreeAsync(p, ctx->stream); }
     sp1b200_err alloc(void** p, size_t bytes) {
-        SP1_CUDA(cudaMallocAsync(p, bytes ? bytes : 4, ctx->stream));
+        SP1_CUDA(cudaMallocFromPoolAsync(p, bytes ? bytes : 4, ctx->pool, ctx->stream));
         ptrs.push_back(*p);
         return nullptr;
     }
@@ -265,15 +265,15 @@ sp1b200_err sp1b200_stacked_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, 
     if (sp1b200_is_device_ptr(dense_any)) {
         c->d_mles = const_cast<uint32_t*>(dense_any);  // borrowed: caller keeps the trace resident (reference: main_virtual_tensor)
     } else {
-        SP1_CUDA(cudaMallocAsync((void**)&c->d_mles, n * sizeof(uint32_t), ctx->stream));
+        SP1_CUDA(cudaMallocFromPoolAsync((void**)&c->d_mles, n * sizeof(uint32_t), ctx->pool, ctx->stream));
         c->owns_mles = true;
         SP1_CUDA(cudaMemcpyAsync(c->d_mles, dense_any, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
-    SP1_CUDA(cudaMallocAsync((void**)&c->d_codeword, M * sizeof(uint32_t), ctx->stream));
+    SP1_CUDA(cudaMallocFromPoolAsync((void**)&c->d_codeword, M * sizeof(uint32_t), ctx->pool, ctx->stream));
     const size_t nd = ((size_t)2 << (log_h + b)) - 1;
-    SP1_CUDA(cudaMallocAsync((void**)&c->d_layers, nd * 8 * sizeof(uint32_t), ctx->stream));
+    SP1_CUDA(cudaMallocFromPoolAsync((void**)&c->d_layers, nd * 8 * sizeof(uint32_t), ctx->pool, ctx->stream));
     uint32_t* d_rc;
-    SP1_CUDA(cudaMallocAsync((void**)&d_rc, 64, ctx->stream));
+    SP1_CUDA(cudaMallocFromPoolAsync((void**)&d_rc, 64, ctx->pool, ctx->stream));
     {
         PhaseTimer t(ctx, "commit.rs_encode");
         SP1_TRY(sp1b200_rs_encode_device(ctx, c->d_mles, ncols, log_h, b, c->d_codeword));

@@ -331,7 +331,7 @@ struct DevFree {
     sp1b200_ctx* ctx; std::vector<void*> ptrs;
     explicit DevFree(sp1b200_ctx* c) : ctx(c) {}
     ~DevFree() { for (void* p : ptrs) cudaFreeAsync(p, ctx->stream); }
-    sp1b200_err alloc(void** p, size_t bytes) { SP1_CUDA(cudaMallocAsync(p, bytes ? bytes : 4, ctx->stream)); ptrs.push_back(*p); return nullptr; }
+    sp1b200_err alloc(void** p, size_t bytes) { SP1_CUDA(cudaMallocFromPoolAsync(p, bytes ? bytes : 4, ctx->pool, ctx->stream)); ptrs.push_back(*p); return nullptr; }
 };
 inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 

@@ -143,15 +143,25 @@ __device__ __forceinline__ void pair_sums(const Row4& x, const Row4& y, const Ex
 }
 
 __device__ __forceinline__ void block_reduce3(Ext a, Ext b, Ext c, uint32_t* __restrict__ partial, const Mail& mail) {
-    __shared__ uint32_t red[12][256];
-    for (int l = 0; l < 4; l++) { red[l][threadIdx.x] = a.c[l]; red[4 + l][threadIdx.x] = b.c[l]; red[8 + l][threadIdx.x] = c.c[l]; }
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s)
-            for (int l = 0; l < 12; l++) red[l][threadIdx.x] = kb::add(red[l][threadIdx.x], red[l][threadIdx.x + s]);
-        __syncthreads();
+    // warp shuffles + one barrier (these kernels are latency-bound on the upper layers: a shared-memory tree costs 8 barriers)
+    __shared__ uint32_t red[12][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t w[12];
+#pragma unroll
+    for (int l = 0; l < 4; l++) { w[l] = a.c[l]; w[4 + l] = b.c[l]; w[8 + l] = c.c[l]; }
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        uint32_t v = w[k];
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) v = kb::add(v, __shfl_down_sync(0xffffffffu, v, sft));
+        if (lane == 0) red[k][warp] = v;
     }
-    if (threadIdx.x < 12) partial[blockIdx.x * 12 + threadIdx.x] = red[threadIdx.x][0];
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        uint32_t v = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); q++) v = kb::add(v, red[threadIdx.x][q]);
+        partial[blockIdx.x * 12 + threadIdx.x] = v;
+    }
     sp1_mail_done(mail);  // `partial` is the mailbox payload: the host transcript polls the flag (ctx.cuh)
 }
 

@@ -128,15 +128,25 @@ __device__ __forceinline__ uint32_t seg_load(const SegTable& t, uint64_t i) {
 }
 
 __device__ __forceinline__ void block_reduce2(Ext a, Ext b, uint32_t* __restrict__ partial, const Mail& mail) {
-    __shared__ uint32_t red[8][256];
-    for (int l = 0; l < 4; l++) { red[l][threadIdx.x] = a.c[l]; red[4 + l][threadIdx.x] = b.c[l]; }
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s)
-            for (int l = 0; l < 8; l++) red[l][threadIdx.x] = kb::add(red[l][threadIdx.x], red[l][threadIdx.x + s]);
-        __syncthreads();
+    // warp shuffles + one barrier (the late rounds are latency-bound)
+    __shared__ uint32_t red[8][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t w[8];
+#pragma unroll
+    for (int l = 0; l < 4; l++) { w[l] = a.c[l]; w[4 + l] = b.c[l]; }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t v = w[k];
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) v = kb::add(v, __shfl_down_sync(0xffffffffu, v, sft));
+        if (lane == 0) red[k][warp] = v;
     }
-    if (threadIdx.x < 8) partial[blockIdx.x * 8 + threadIdx.x] = red[threadIdx.x][0];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        uint32_t v = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); q++) v = kb::add(v, red[threadIdx.x][q]);
+        partial[blockIdx.x * 8 + threadIdx.x] = v;
+    }
     sp1_mail_done(mail);  // `partial` is the mailbox payload (ctx.cuh): the host transcript polls instead of copy + synchronise
 }
 

@@ -115,7 +115,7 @@ void sp1b200_ctx_destroy(sp1b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_TH); cudaFree(c->d_TL); cudaFree(c->d_TS);
+    cudaFree(c->d_TH); cudaFree(c->d_TL);
     cudaFree(c->d_mail_counter);
     if (c->h_mail) cudaFreeHost(c->h_mail);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }

@@ -21,7 +21,6 @@ struct sp1b200_ctx {
     // TH[i] = w^(i * 2^12), TL[j] = w^j  with w = two-adic generator of order 2^24 (Montgomery words)
     uint32_t* d_TH = nullptr;
     uint32_t* d_TL = nullptr;
-    uint2* d_TS = nullptr;   // Shoup form of TH for the NTT butterflies: {canonical w, floor(w 2^32 / p)}
     uint64_t launches = 0;
     bool force_generic_ntt = false;  // SP1B200_GENERIC_NTT=1: reference (slow) kernels, used to cross-check the fast path
     std::map<std::string, float> phase_ms;

@@ -24,17 +24,13 @@ __device__ __forceinline__ uint32_t root_pow(const uint32_t* __restrict__ TH, co
     return lo ? kb::mul(hi, __ldg(TL + lo)) : hi;
 }
 
-__global__ void init_tables_kernel(uint32_t* TH, uint32_t* TL, uint2* TS) {
+__global__ void init_tables_kernel(uint32_t* TH, uint32_t* TL) {
     // w = 3^127 generates the 2^24-th roots (sppark/ntt/parameters/koala_bear.h:5-36, checked in tests)
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 4096) return;
     uint32_t w = kb::pow(kb::to_monty_c(3), 127);
     TL[i] = kb::pow(w, i);
     TH[i] = kb::pow(w, (uint64_t)i << 12);
-    // Shoup companion of TH[i]: multiplying a Montgomery word x by the CANONICAL twiddle gives the same word as the
-    // Montgomery product with TH[i]; the precomputed quotient turns the reduction into one high product
-    const uint32_t wc = kb::to_canonical(TH[i]);
-    TS[i] = make_uint2(wc, (uint32_t)((((uint64_t)wc) << 32) / kb::P));
 }
 
 // ---- generic step A: coset expansion + size-2^L1 DIF over the strided (hi) axis ---------------------------
@@ -116,19 +112,9 @@ __global__ void rs_step_b_generic(uint32_t* __restrict__ buf, int L1, int L2, in
 
 // (a - c) * w with the difference left unreduced in (0, 2p): valid Montgomery operand since w < p
 __device__ __forceinline__ uint32_t submul(uint32_t a, uint32_t c, uint32_t w) { return kb::mul(a - c + kb::P, w); }
-// Shoup form of the same product (w.x canonical twiddle, w.y = floor(w 2^32 / p)): for any 32-bit d,
-// d w - floor(d w.y / 2^32) p lies in [0, 2p); one high product + two low products instead of two of each (section 3.1 of DESIGN.md:
-// 0.061 vs 0.090 SM-clocks per lane)
-__device__ __forceinline__ uint32_t submul(uint32_t a, uint32_t c, uint2 w) {
-    const uint32_t d = a - c + kb::P;
-    const uint32_t q = __umulhi(d, w.y);
-    const uint32_t r = d * w.x - q * kb::P;
-    return kb::umin(r, r - kb::P);
-}
 
 // in-place radix-8 decimation-in-frequency butterfly on v[0..8) (v[j], j bit 2 = most significant of the 3 index bits)
-template <class TW>
-__device__ __forceinline__ void dif8(uint32_t (&v)[8], const TW (&wA)[4], const TW (&wB)[2], TW wC) {
+__device__ __forceinline__ void dif8(uint32_t (&v)[8], const uint32_t (&wA)[4], const uint32_t (&wB)[2], uint32_t wC) {
 #pragma unroll
     for (int j = 0; j < 4; j++) { uint32_t a = v[j], c = v[j + 4]; v[j] = kb::add(a, c); v[j + 4] = submul(a, c, wA[j]); }
 #pragma unroll
@@ -141,8 +127,8 @@ __device__ __forceinline__ void dif8(uint32_t (&v)[8], const TW (&wA)[4], const 
 
 // twiddles for a radix-8 pass whose top stage has 2^s points and whose elements are spaced `stride` apart:
 // local element j sits at offset j*stride + low inside its 2^s block  (stride = 2^(s-3))
-template <class TW>
-__device__ __forceinline__ void load_tw8(const TW* __restrict__ TH, int s, uint32_t low, TW (&wA)[4], TW (&wB)[2], TW& wC) {
+__device__ __forceinline__ void load_tw8(const uint32_t* __restrict__ TH, int s, uint32_t low, uint32_t (&wA)[4], uint32_t (&wB)[2],
+                                         uint32_t& wC) {
     const uint32_t stride = 1u << (s - 3);
 #pragma unroll
     for (int j = 0; j < 4; j++) wA[j] = __ldg(TH + ((j * stride + low) << (12 - s)));
@@ -155,7 +141,7 @@ __device__ __forceinline__ void load_tw8(const TW* __restrict__ TH, int s, uint3
 __device__ __forceinline__ int swzB(int e) { return e ^ (((e >> 5) & 7) << 2); }
 
 __global__ void __launch_bounds__(256) rs_step_b_2048(uint32_t* __restrict__ buf, int L1, int b, const uint32_t* __restrict__ TH,
-                                                      const uint32_t* __restrict__ TL, const uint2* __restrict__ TS) {
+                                                      const uint32_t* __restrict__ TL) {
     __shared__ uint32_t sm[2048];
     constexpr int L2 = 11;
     const int L = L1 + L2;
@@ -164,8 +150,7 @@ __global__ void __launch_bounds__(256) rs_step_b_2048(uint32_t* __restrict__ buf
     const uint32_t ka = (L1 + b) ? (__brev(q) >> (32 - (L1 + b))) : 0;
     uint32_t* row = buf + (size_t)blockIdx.y * M + ((size_t)q << L2);
     const int t = threadIdx.x;
-    uint32_t v[8];
-    uint2 wA[4], wB[2], wC;
+    uint32_t v[8], wA[4], wB[2], wC;
     // pass 1: bits 10..8, straight from global, with the inter-step twist omega^(lo * ka)
 #pragma unroll
     for (int j = 0; j < 8; j++) v[j] = row[j * 256 + t];
@@ -176,7 +161,7 @@ __global__ void __launch_bounds__(256) rs_step_b_2048(uint32_t* __restrict__ buf
 #pragma unroll
         for (int j = 0; j < 8; j++) { v[j] = kb::mul(v[j], tw); if (j < 7) tw = kb::mul(tw, step); }
     }
-    load_tw8(TS, 11, t, wA, wB, wC);
+    load_tw8(TH, 11, t, wA, wB, wC);
     dif8(v, wA, wB, wC);
 #pragma unroll
     for (int j = 0; j < 8; j++) sm[swzB(j * 256 + t)] = v[j];
@@ -186,7 +171,7 @@ __global__ void __launch_bounds__(256) rs_step_b_2048(uint32_t* __restrict__ buf
         const int low = t & 31, hib = t >> 5;
 #pragma unroll
         for (int j = 0; j < 8; j++) v[j] = sm[swzB(hib * 256 + j * 32 + low)];
-        load_tw8(TS, 8, low, wA, wB, wC);
+        load_tw8(TH, 8, low, wA, wB, wC);
         dif8(v, wA, wB, wC);
 #pragma unroll
         for (int j = 0; j < 8; j++) sm[swzB(hib * 256 + j * 32 + low)] = v[j];
@@ -197,14 +182,14 @@ __global__ void __launch_bounds__(256) rs_step_b_2048(uint32_t* __restrict__ buf
         const int low = t & 3, hib = t >> 2;
 #pragma unroll
         for (int j = 0; j < 8; j++) v[j] = sm[swzB(hib * 32 + j * 4 + low)];
-        load_tw8(TS, 5, low, wA, wB, wC);
+        load_tw8(TH, 5, low, wA, wB, wC);
         dif8(v, wA, wB, wC);
 #pragma unroll
         for (int j = 0; j < 8; j++) sm[swzB(hib * 32 + j * 4 + low)] = v[j];
     }
     __syncthreads();
     // pass 4: bits 1..0 (radix 4, only non-trivial twiddle is the 4th root), two groups per thread, 16-byte I/O
-    const uint2 w4 = __ldg(TS + 1024);
+    const uint32_t w4 = __ldg(TH + 1024);
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const int g = t + k * 256;
@@ -221,8 +206,7 @@ __device__ __forceinline__ int swzA(int e) { return e ^ (((e >> 7) & 1) << 4); }
 
 template <int L1>
 __global__ void __launch_bounds__(1 << L1) rs_step_a_fast(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int L2, int b,
-                                                          const uint32_t* __restrict__ TH, const uint32_t* __restrict__ TL,
-                                                          const uint2* __restrict__ TS) {
+                                                          const uint32_t* __restrict__ TH, const uint32_t* __restrict__ TL) {
     static_assert(L1 % 3 == 1 && L1 >= 7, "L1 = 3k+1, at least two radix-8 passes");
     constexpr int NP = L1 / 3;           // radix-8 passes; the last stage (hi bit 0) is a warp shuffle
     constexpr int TILE = 8 << L1;
@@ -233,8 +217,7 @@ __global__ void __launch_bounds__(1 << L1) rs_step_a_fast(const uint32_t* __rest
     uint32_t* col_out = out + (size_t)blockIdx.y * M;
     const uint32_t lo0 = blockIdx.x * 8;
     const int u = threadIdx.x, lo = u & 7, x = u >> 3;  // x: low L1-3 bits of hi in pass-1 layout
-    uint32_t src[8], v[8];
-    uint2 wA[4], wB[2], wC;
+    uint32_t src[8], v[8], wA[4], wB[2], wC;
 #pragma unroll
     for (int j = 0; j < 8; j++) src[j] = col_in[((size_t)(j * (1 << (L1 - 3)) + x) << L2) + lo0 + lo];
     const int sh = 24 - L1 - b;
@@ -251,7 +234,7 @@ __global__ void __launch_bounds__(1 << L1) rs_step_a_fast(const uint32_t* __rest
             for (int j = 0; j < 8; j++) { v[j] = kb::mul(src[j], tw); if (j < 7) tw = kb::mul(tw, step); }
         }
         // pass 0: hi bits L1-1 .. L1-3
-        load_tw8(TS, L1, x, wA, wB, wC);
+        load_tw8(TH, L1, x, wA, wB, wC);
         dif8(v, wA, wB, wC);
 #pragma unroll
         for (int j = 0; j < 8; j++) sm[swzA(j * (TILE / 8) + u)] = v[j];
@@ -265,7 +248,7 @@ __global__ void __launch_bounds__(1 << L1) rs_step_a_fast(const uint32_t* __rest
             const int stride = 8 << nlow;
 #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = sm[swzA(base + j * stride)];
-            load_tw8(TS, hb + 1, low, wA, wB, wC);
+            load_tw8(TH, hb + 1, low, wA, wB, wC);
             dif8(v, wA, wB, wC);
             if (k < NP - 1) {
 #pragma unroll
@@ -294,15 +277,14 @@ static sp1b200_err launch_step_a_fast(sp1b200_ctx* ctx, const uint32_t* in, uint
     const size_t smem = 2 * (size_t)(8 << L1) * sizeof(uint32_t);
     SP1_CUDA(cudaFuncSetAttribute(rs_step_a_fast<L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g((1u << L2) / 8, nc);
-    SP1_LAUNCH(ctx, rs_step_a_fast<L1>, g, 1 << L1, smem, in, out, L2, b, ctx->d_TH, ctx->d_TL, ctx->d_TS);
+    SP1_LAUNCH(ctx, rs_step_a_fast<L1>, g, 1 << L1, smem, in, out, L2, b, ctx->d_TH, ctx->d_TL);
     return nullptr;
 }
 
 sp1b200_err sp1b200_init_tables(sp1b200_ctx* ctx) {
     SP1_CUDA(cudaMalloc(&ctx->d_TH, 4096 * sizeof(uint32_t)));
     SP1_CUDA(cudaMalloc(&ctx->d_TL, 4096 * sizeof(uint32_t)));
-    SP1_CUDA(cudaMalloc(&ctx->d_TS, 4096 * sizeof(uint2)));
-    SP1_LAUNCH(ctx, init_tables_kernel, 16, 256, 0, ctx->d_TH, ctx->d_TL, ctx->d_TS);
+    SP1_LAUNCH(ctx, init_tables_kernel, 16, 256, 0, ctx->d_TH, ctx->d_TL);
     return nullptr;
 }
 
@@ -340,7 +322,7 @@ sp1b200_err sp1b200_rs_encode_device(sp1b200_ctx* ctx, const uint32_t* d_msg, ui
         if (fast && L1 == 10) SP1_TRY(launch_step_a_fast<10>(ctx, d_msg + c0 * n, d_out + c0 * M, L2, b, nc));
         else if (fast && L1 == 7) SP1_TRY(launch_step_a_fast<7>(ctx, d_msg + c0 * n, d_out + c0 * M, L2, b, nc));
         else SP1_LAUNCH(ctx, rs_step_a_generic, gA, threadsA, smemA, d_msg + c0 * n, d_out + c0 * M, L1, L2, b, T, ctx->d_TH, ctx->d_TL);
-        if (fast) SP1_LAUNCH(ctx, rs_step_b_2048, gB, 256, 0, d_out + c0 * M, L1, b, ctx->d_TH, ctx->d_TL, ctx->d_TS);
+        if (fast) SP1_LAUNCH(ctx, rs_step_b_2048, gB, 256, 0, d_out + c0 * M, L1, b, ctx->d_TH, ctx->d_TL);
         else SP1_LAUNCH(ctx, rs_step_b_generic, gB, threadsB, smemB, d_out + c0 * M, L1, L2, b, ctx->d_TH, ctx->d_TL);
     }
     return nullptr;

@@ -58,6 +58,13 @@ sp1b200_err sp1b200_malloc(sp1b200_ctx* ctx, size_t bytes, void** d_out);
 sp1b200_err sp1b200_free(sp1b200_ctx* ctx, void* d_ptr);
 sp1b200_err sp1b200_memcpy_h2d(sp1b200_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 sp1b200_err sp1b200_memcpy_d2h(sp1b200_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* Row-major chip traces -> the dense column-major layout every commit / prove entry point takes (TraceDenseData,
+ * sp1-gpu/crates/utils/src/traces.rs:48-75).  The reference's CPU trace generator yields one row-major [rows x cols] matrix
+ * per chip (crates/hypercube/src/prover/trace.rs:126-201) and its GPU prover transposes on the device; this is that step.
+ * rows_any: the tables back to back, each row-major (host or device); d_dense_out: device buffer of the same total size, tables
+ * back to back, each column-major. */
+sp1b200_err sp1b200_pack_row_major(sp1b200_ctx* ctx, const uint32_t* rows_any, uint32_t n_tables, const uint64_t* rows,
+                                   const uint64_t* cols, uint32_t* d_dense_out);
 /* Double-buffered asynchronous upload (replaces the host->device trace transfer the reference does per shard in
  * sp1-gpu/crates/jagged_tracegen: traces of shard k+1 are moved while shard k is proven).  Copies n_words words from
  * (ideally pinned) host memory into library-owned slot 0 or 1 on a separate copy stream and returns the slot's device

@@ -54,7 +54,7 @@ def load():
 # every symbol include/sp1b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 ERR_FUNCS = [
     "sp1b200_ctx_create", "sp1b200_ctx_sync", "sp1b200_malloc", "sp1b200_free", "sp1b200_memcpy_h2d",
-    "sp1b200_memcpy_d2h", "sp1b200_upload_begin", "sp1b200_poseidon2_permute", "sp1b200_rs_encode", "sp1b200_merkle_commit", "sp1b200_grind",
+    "sp1b200_memcpy_d2h", "sp1b200_upload_begin", "sp1b200_pack_row_major", "sp1b200_poseidon2_permute", "sp1b200_rs_encode", "sp1b200_merkle_commit", "sp1b200_grind",
     "sp1b200_stacked_commit", "sp1b200_stacked_prove", "sp1b200_jagged_commit", "sp1b200_jagged_column_claims",
     "sp1b200_jagged_prove", "sp1b200_machine_create", "sp1b200_zerocheck", "sp1b200_logup_gkr", "sp1b200_prove_shard",
 ]
@@ -253,6 +253,13 @@ class Lib:
         self._chk(self.L.sp1b200_prove_shard(self.ctx, machine, prep_round, _ptr(main_dense), H, NM, _ptr(pv), C.c_uint32(pv.size),
                                              _ptr(rw), _ptr(challenger_state), _ptr(out), C.c_uint64(cap_words), C.byref(nw)))
         return out[:nw.value].copy()
+
+    def pack_row_major(self, rows_any, shapes, d_dense_out):
+        """tables back to back, each row-major [rows x cols] -> device buffer with each table column-major"""
+        n = len(shapes)
+        R = (C.c_uint64 * n)(*[int(r) for r, _ in shapes])
+        Cc = (C.c_uint64 * n)(*[int(c) for _, c in shapes])
+        self._chk(self.L.sp1b200_pack_row_major(self.ctx, _ptr(rows_any), C.c_uint32(n), R, Cc, _ptr(d_dense_out)))
 
     def upload_begin(self, host_array, slot):
         """async H2D of a (pinned) host array into upload slot 0/1 -> device pointer (int) to pass as main_dense"""

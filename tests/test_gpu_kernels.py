@@ -107,3 +107,23 @@ def test_device_pointer_io(lib):
     root, commit = lib.merkle_commit(d_out, ncols, log_h + 2)
     _, ocommit = O.merkle_commit(O.rs_encode(msg, 2))
     assert (commit == ocommit).all()
+
+
+def test_pack_row_major_is_the_dense_layout(lib):
+    """row-major chip traces (the CPU trace generator's layout) -> dense column-major: equals numpy's transpose, ragged shapes,
+    an empty table in the middle, widths and heights that are not multiples of the 32 x 32 tile; host and device inputs."""
+    import torch
+    rng = np.random.default_rng(77)
+    shapes = [(96, 5), (1, 1), (0, 7), (33, 33), (4099, 70), (64, 246)]
+    tabs = [O.rand_field(rng, (r, c)) for r, c in shapes]
+    flat_rows = np.ascontiguousarray(np.concatenate([t.reshape(-1) for t in tabs]))
+    expect = np.concatenate([np.ascontiguousarray(t.T).reshape(-1) for t in tabs])
+    d_out = torch.zeros(flat_rows.size, dtype=torch.int32, device="cuda")
+    lib.pack_row_major(flat_rows, shapes, d_out)
+    lib.sync()
+    assert (d_out.cpu().numpy().view(np.uint32) == expect).all()
+    d_in = torch.from_numpy(flat_rows.view(np.int32)).cuda()
+    d_out2 = torch.zeros_like(d_out)
+    lib.pack_row_major(d_in, shapes, d_out2)
+    lib.sync()
+    assert torch.equal(d_out, d_out2)

@@ -68,8 +68,11 @@ class Asm:
         return w
 
 
-def synth_chip(groups, with_prep, kconst=7):
-    """-> (machine words for this chip, main_w, prep_w)"""
+def synth_chip(groups, with_prep, kconst=7, deep=False):
+    """-> (machine words for this chip, main_w, prep_w).
+    deep=True emits the SAME constraints in an order with long-lived intermediates (all products a_g b_g first, consumed in
+    reverse order afterwards): the register pressure of the program grows with `groups`, which exercises the larger
+    register-file tiers of the zerocheck kernels (the flat order needs a handful of registers whatever the chip size)."""
     a = Asm()
     main_w = 6 * groups + (1 if with_prep else 0)
     prep_w = 1 if with_prep else 0
@@ -77,13 +80,27 @@ def synth_chip(groups, with_prep, kconst=7):
     kc = a.const(kconst)
     one = a.const(1)
     kpv = a.op(MUL, kc, pv0)
-    for g in range(groups):
-        A, B, Cc, D, E, Fc = (a.leaf(LEAF_MAIN, 6 * g + i) for i in range(6))
-        ab = a.op(MUL, A, B)
+
+    def tail(g, ab, A=None):
+        Cc, D, E, Fc = (a.leaf(LEAF_MAIN, 6 * g + i) for i in range(2, 6))
+        if A is None:
+            A = a.leaf(LEAF_MAIN, 6 * g)
         a.assert_zero(a.op(SUB, Cc, ab))                       # c - a b
         a.assert_zero(a.op(MUL, D, a.op(SUB, D, one)))         # d (d - 1)
         a.assert_zero(a.op(SUB, E, a.op(MUL, ab, D)))          # e - a b d   (degree 3)
         a.assert_zero(a.op(SUB, Fc, a.op(ADD, A, kpv)))        # f - (a + K pv0)
+
+    if deep:
+        abs_ = []
+        for g in range(groups):
+            A, B = a.leaf(LEAF_MAIN, 6 * g), a.leaf(LEAF_MAIN, 6 * g + 1)
+            abs_.append(a.op(MUL, A, B))
+        for g in reversed(range(groups)):
+            tail(g, abs_[g])
+    else:
+        for g in range(groups):
+            A, B = a.leaf(LEAF_MAIN, 6 * g), a.leaf(LEAF_MAIN, 6 * g + 1)
+            tail(g, a.op(MUL, A, B), A)
     if with_prep:
         G = a.leaf(LEAF_PREP, 0)
         H = a.leaf(LEAF_MAIN, 6 * groups)

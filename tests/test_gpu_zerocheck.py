@@ -24,7 +24,10 @@ def _ext_add(a, b):
     ([(5, 1, False), (0, 2, False), (6, 1, True)], 3),
     ([(1, 1, False), (2, 1, True)], 4),
     ([(32, 3, True), (96, 2, False), (128, 1, False)], 7),
-    ([(4096, 2, True), (1000, 12, False), (0, 1, False), (2048 + 32, 5, False)], 13),   # 12 groups -> 288 registers (tier 1024)
+    ([(4096, 2, True), (1000, 12, False), (0, 1, False), (2048 + 32, 5, False)], 13),
+    # long-lived intermediates: register pressure ~ groups -> every register-file tier (<= 8, <= 16, <= 32 in shared memory,
+    # local-memory fallback above) in one proof, next to a flat chip
+    ([(512, 6, False, True), (300, 14, True, True), (1024, 28, False, True), (96, 40, False, True), (2048, 3, True)], 12),
 ])
 def test_zerocheck_matches_oracle(spec, mlr):
     import torch

@@ -93,6 +93,15 @@ def test_constraint_lowering_preserves_the_row_polynomial():
             assert regs <= 16, (groups, wp, window, regs)
 
 
+def test_constraint_lowering_pressure_tracks_live_values():
+    """deep programs (all products first, consumed in reverse): the lowered pressure follows the live set, results unchanged"""
+    from sp1_b200 import synth_air as SA
+    for groups in (6, 14, 28, 40):
+        words, main_w, prep_w = SA.synth_chip(groups, False, deep=True)
+        regs, _ = _check_lowering(words, main_w, prep_w, words[2], seed=groups)
+        assert groups <= regs <= groups + 8, (groups, regs)
+
+
 def test_constraint_lowering_handles_register_reuse_dead_code_and_leaf_asserts():
     from sp1_b200 import synth_air as SA
     a = SA.Asm()

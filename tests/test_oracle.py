@@ -237,11 +237,11 @@ def test_jagged_pcs_roundtrip(shapes_rounds, log_stack, max_log_rows):
 
 
 def _synth_machine(rng, spec, pv0=12345):
-    """spec: list of (height, groups, with_prep)"""
+    """spec: list of (height, groups, with_prep[, deep])"""
     from sp1_b200 import synth_air as SA
     words, mains, preps, heights = [], [], [], []
-    for h, g, wp in spec:
-        w, _, _ = SA.synth_chip(g, wp)
+    for h, g, wp, *rest in spec:
+        w, _, _ = SA.synth_chip(g, wp, deep=bool(rest and rest[0]))
         words.append(w)
         m, p = SA.synth_trace(rng, h, g, wp, pv0)
         mains.append(m); preps.append(p); heights.append(h)

@@ -549,7 +549,8 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     SP1_CUDA(cudaMemsetAsync(d_final, 0, (wsum ? wsum : 1) * 16, st));
     auto launch_sum = [&](const Launch& Lc, bool ext, uint32_t* part) -> sp1b200_err {
         auto go = [&](auto kern, size_t smem) -> sp1b200_err {
-            if (smem > 48 * 1024) SP1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // the static reduction buffer counts against the 48 KiB default as well: opt in early
+            if (smem > 32 * 1024) SP1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SP1_LAUNCH(ctx, kern, Lc.blocks, ZC_BLOCK, smem, d_jobs + Lc.job0, (int)Lc.n_jobs, m->d_chips, d_pv, d_gw, d_E[ecur], part);
             return nullptr;
         };

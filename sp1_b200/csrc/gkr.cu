@@ -136,10 +136,10 @@ __device__ __forceinline__ void pair_sums(const Row4& x, const Row4& y, const Ex
     Ext t0 = kb::ext_add(kb::ext_mul(lambda, kb::ext_add(kb::ext_mul(x.d0, x.n1), kb::ext_mul(x.d1, x.n0))), kb::ext_mul(x.d0, x.d1));
     Ext D0 = kb::ext_add(x.d0, y.d0), D1 = kb::ext_add(x.d1, y.d1), N0 = kb::ext_add(x.n0, y.n0), N1 = kb::ext_add(x.n1, y.n1);
     Ext th = kb::ext_add(kb::ext_mul(lambda, kb::ext_add(kb::ext_mul(D0, N1), kb::ext_mul(D1, N0))), kb::ext_mul(D0, D1));
-    Ext ers = kb::ext_add(er0, er1);
-    s0 = kb::ext_add(s0, kb::ext_mul(kb::ext_mul(e, t0), er0));
-    sh = kb::ext_add(sh, kb::ext_mul(kb::ext_mul(e, th), ers));
-    se = kb::ext_add(se, kb::ext_mul(e, ers));
+    const Ext ee0 = kb::ext_mul(e, er0), ees = kb::ext_mul(e, kb::ext_add(er0, er1));  // shared by the three sums
+    s0 = kb::ext_add(s0, kb::ext_mul(ee0, t0));
+    sh = kb::ext_add(sh, kb::ext_mul(ees, th));
+    se = kb::ext_add(se, ees);
 }
 
 __device__ __forceinline__ void block_reduce3(Ext a, Ext b, Ext c, uint32_t* __restrict__ partial, const Mail& mail) {

@@ -100,16 +100,20 @@ __global__ void __launch_bounds__(256) column_claims_kernel(const uint32_t* __re
     if (threadIdx.x < 4) out[c * 4 + threadIdx.x] = red[threadIdx.x][0];
 }
 
-// jagged little polynomial: ext[i] = col_eq[c(i)] * row_eq[i - prefix[c(i)]] for i < prefix[ncols], else 0
-__global__ void __launch_bounds__(256) jagged_poly_kernel(const uint64_t* __restrict__ prefix, uint32_t ncols, const uint32_t* __restrict__ col_eq,
-                                                          const uint32_t* __restrict__ row_eq, uint64_t N, uint32_t* __restrict__ ext) {
+// jagged little polynomial: ext[i] = col_eq[c(i)] * row_eq[i - prefix[c(i)]] for i < prefix[ncols], else 0.
+// c(i) = the last column with prefix[c] <= i (zero-height columns share a prefix value: the last one has the non-empty range).
+// start[i >> JP_SHIFT] (built on the host from the same prefix sums) is a column at or before c(i), so the search is a short
+// forward walk instead of a binary search per element.
+constexpr int JP_SHIFT = 12;
+__global__ void __launch_bounds__(256) jagged_poly_kernel(const uint64_t* __restrict__ prefix, uint32_t ncols, const uint32_t* __restrict__ start,
+                                                          const uint32_t* __restrict__ col_eq, const uint32_t* __restrict__ row_eq, uint64_t N,
+                                                          uint32_t* __restrict__ ext) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     Ext v = kb::ext_zero();
     if (i < prefix[ncols]) {
-        // largest c with prefix[c] <= i  (zero-height columns share a prefix value: take the last, whose range is non-empty)
-        uint32_t lo = 0, hi = ncols;  // invariant prefix[lo] <= i < prefix[hi]
-        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (prefix[mid] <= i) lo = mid; else hi = mid; }
+        uint32_t lo = start[i >> JP_SHIFT];
+        while (lo + 1 < ncols && prefix[lo + 1] <= i) lo++;
         v = kb::ext_mul(kb::ext_load(col_eq + 4 * lo), kb::ext_load(row_eq + 4 * (i - prefix[lo])));
     }
     kb::ext_store(ext + 4 * i, v);
@@ -615,6 +619,19 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
     SP1_LAUNCH(ctx, eq_table_kernel, blocks_for((uint64_t)1 << mlr), 256, 0, d_zrow, (int)mlr, d_roweq);
     SP1_TRY(mem.alloc((void**)&d_prefix, prefix.size() * 8));
     SP1_CUDA(cudaMemcpyAsync(d_prefix, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice, st));
+    // start[b] = last column with prefix <= b << JP_SHIFT (two-pointer walk over the blocks of the real area)
+    std::vector<uint32_t> jp_start((size_t)((prefix.back() >> JP_SHIFT) + 1));
+    {
+        uint32_t c = 0;
+        for (size_t b = 0; b < jp_start.size(); b++) {
+            const uint64_t i0 = (uint64_t)b << JP_SHIFT;
+            while (c + 1 < total_cols && prefix[c + 1] <= i0) c++;
+            jp_start[b] = c;
+        }
+    }
+    uint32_t* d_jp_start;
+    SP1_TRY(mem.alloc((void**)&d_jp_start, jp_start.size() * 4));
+    SP1_CUDA(cudaMemcpyAsync(d_jp_start, jp_start.data(), jp_start.size() * 4, cudaMemcpyHostToDevice, st));
     SP1_TRY(mem.alloc((void**)&d_ext, N * 16));
     SP1_TRY(mem.alloc((void**)&d_ext2, (N / 2) * 16));
     SP1_TRY(mem.alloc((void**)&d_b, (N / 2) * 16));
@@ -624,7 +641,7 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
     d_partial = sp1b200_mail_dev(ctx);  // the round kernels post their block partials straight into the mailbox
     {
         PhaseTimer t(ctx, "jagged.little_poly");
-        SP1_LAUNCH(ctx, jagged_poly_kernel, blocks_for(N), 256, 0, d_prefix, (uint32_t)total_cols, d_coleq, d_roweq, N, d_ext);
+        SP1_LAUNCH(ctx, jagged_poly_kernel, blocks_for(N), 256, 0, d_prefix, (uint32_t)total_cols, d_jp_start, d_coleq, d_roweq, N, d_ext);
         t.stop();
     }
     SegTable seg{};

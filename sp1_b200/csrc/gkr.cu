@@ -373,25 +373,6 @@ struct DevFree {
 };
 inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
-std::vector<E4> host_interp(const std::vector<E4>& xs, const std::vector<E4>& ys) {
-    size_t n = xs.size();
-    std::vector<E4> res(n);
-    for (size_t i = 0; i < n; i++) {
-        std::vector<E4> num{ys[i]};
-        E4 den = E4::one();
-        for (size_t j = 0; j < n; j++) {
-            if (j == i) continue;
-            den = den * (xs[i] - xs[j]);
-            std::vector<E4> nx(num.size() + 1);
-            for (size_t k = 0; k < num.size(); k++) { nx[k + 1] = nx[k + 1] + num[k]; nx[k] = nx[k] - num[k] * xs[j]; }
-            num.swap(nx);
-        }
-        E4 dinv = hf::inv(den);
-        for (size_t k = 0; k < num.size(); k++) res[k] = res[k] + num[k] * dinv;
-    }
-    return res;
-}
-E4 host_poly_eval(const std::vector<E4>& c, const E4& x) { E4 r; for (size_t i = c.size(); i-- > 0;) r = r * x + c[i]; return r; }
 inline Ext toExt(const E4& e) { return Ext{{e.c[0], e.c[1], e.c[2], e.c[3]}}; }
 
 const uint32_t* parse_vcol(const uint32_t* b, HostInteractions& H) {

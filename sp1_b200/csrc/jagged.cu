@@ -450,14 +450,6 @@ __global__ void __launch_bounds__(128) bp_update_kernel(const uint8_t* __restric
     for (int s = 0; s < 4; s++) kb::ext_store(P + ((size_t)k * 4 + s) * 4, out[s]);
 }
 
-// inter[k] *= alpha * x + (1 - alpha) * (1 - x),  x = bits[k][dim - 1 - round]
-__global__ void bp_fix_kernel(const uint8_t* __restrict__ bits, uint32_t nk, uint32_t dim, uint32_t round, Ext alpha, uint32_t* __restrict__ inter) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nk) return;
-    Ext f = bits[(size_t)k * dim + dim - 1 - round] ? alpha : kb::ext_sub(kb::ext_one(), alpha);
-    kb::ext_store(inter + 4 * k, kb::ext_mul(kb::ext_load(inter + 4 * k), f));
-}
-
 // p(x) through (0, y0), (1, y1), (1/2, yh): coefficients c0, c1, c2
 inline void interp_0_1_half(const E4& y0, const E4& y1, const E4& yh, E4 c[3]) {
     const uint32_t two = hf::to_monty(2), three = hf::to_monty(3), four = hf::to_monty(4);

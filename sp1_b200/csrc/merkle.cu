@@ -55,19 +55,6 @@ __global__ void __launch_bounds__(256) leaf_hash_kernel(const uint32_t* __restri
     store_digest(digests + i * 8, s);
 }
 
-// parents[j] = compress(children[2j], children[2j+1])
-__global__ void __launch_bounds__(256) compress_layer_kernel(const uint32_t* __restrict__ children, uint32_t* __restrict__ parents,
-                                                             uint64_t n_parents) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_parents) return;
-    uint32_t s[16];
-    const uint4* p = reinterpret_cast<const uint4*>(children + j * 16);
-#pragma unroll
-    for (int k = 0; k < 4; k++) { uint4 v = __ldg(p + k); s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w; }
-    p2::permute(s);
-    store_digest(parents + j * 8, s);
-}
-
 // ---- subtree kernel: up to 9 compress levels per launch ------------------------------------------------------------------------
 // A block takes 512 consecutive digests of layer k0 (or, MODE 1, the 512 FRI leaves it first hashes from the limb-major
 // codeword: leaf i = hash(cw[2i] limbs, cw[2i+1] limbs), one permutation) and climbs: level j halves the active threads, parents

@@ -190,24 +190,6 @@ __global__ void fold_codeword_kernel(const uint32_t* __restrict__ cw, int log_m,
     for (int l = 0; l < 4; l++) out[l * mo + i] = f.c[l];
 }
 
-// FRI-round leaves: leaf i = hash(cw[2i] limbs, cw[2i+1] limbs) -- one permutation (8 words = rate)
-__global__ void __launch_bounds__(256) fri_leaf_hash_kernel(const uint32_t* __restrict__ cw, uint64_t m, uint32_t* __restrict__ digests) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m / 2) return;
-    uint32_t s[16];
-#pragma unroll
-    for (int l = 0; l < 4; l++) {
-        uint2 v = *reinterpret_cast<const uint2*>(cw + l * m + 2 * i);
-        s[l] = v.x; s[4 + l] = v.y;
-    }
-#pragma unroll
-    for (int k = 8; k < 16; k++) s[k] = 0;
-    p2::permute(s);
-    uint4* p = reinterpret_cast<uint4*>(digests + i * 8);
-    p[0] = make_uint4(s[0], s[1], s[2], s[3]);
-    p[1] = make_uint4(s[4], s[5], s[6], s[7]);
-}
-
 // values[q][c] = codeword[c][idx[q]]
 __global__ void gather_columns_kernel(const uint32_t* __restrict__ cw, uint64_t ncols, uint64_t M, const uint32_t* __restrict__ idx,
                                       uint32_t nq, uint32_t* __restrict__ out) {

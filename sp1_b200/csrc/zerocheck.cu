@@ -297,26 +297,6 @@ E4 host_eval_zero_row(const HostProg& p, const uint32_t* pv, const std::vector<E
     return acc;
 }
 
-std::vector<E4> host_interpolate(const std::vector<E4>& xs, const std::vector<E4>& ys) {
-    size_t n = xs.size();
-    std::vector<E4> res(n);
-    for (size_t i = 0; i < n; i++) {
-        std::vector<E4> num{ys[i]};
-        E4 den = E4::one();
-        for (size_t j = 0; j < n; j++) {
-            if (j == i) continue;
-            den = den * (xs[i] - xs[j]);
-            std::vector<E4> nx(num.size() + 1);
-            for (size_t k = 0; k < num.size(); k++) { nx[k + 1] = nx[k + 1] + num[k]; nx[k] = nx[k] - num[k] * xs[j]; }
-            num.swap(nx);
-        }
-        E4 dinv = hf::inv(den);
-        for (size_t k = 0; k < num.size(); k++) res[k] = res[k] + num[k] * dinv;
-    }
-    return res;
-}
-E4 host_eval_poly(const std::vector<E4>& c, const E4& x) { E4 r; for (size_t i = c.size(); i-- > 0;) r = r * x + c[i]; return r; }
-
 struct VGeq {
     uint32_t threshold = 0; E4 geq_c, eq_c;
     VGeq fix_last(const E4& a) const {

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Generate tests/golden/shard_proofs.json: small whole-shard proofs produced by the CPU oracle (oracle/liboracle.so) on seeded
+synthetic machines.  The reference holds no golden vectors for this path and cannot be built in this image,
+so these fixtures pin the ORACLE against accidental change (and give the GPU suite a committed, oracle-independent target):
+every entry stores the preprocessed commitment, the main commitment, the final challenger state, the section lengths and a
+SHA-256 of the proof words; the first and last 8 words of every section are stored in clear for debugging.
+
+  python tools/gen_golden_proofs.py            # rewrites tests/golden/shard_proofs.json
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from tests import oracle_lib as O  # noqa: E402
+from tests.test_oracle import _synth_machine_gkr  # noqa: E402
+
+CASES = [
+    # name, spec [(height, groups, with_prep)], log_stack, max_log_rows, seed, queries, pow, batch_pow, gkr_pow
+    ("one_chip_full_height", [(8, 1, False)], 3, 3, 101, 4, 3, 2, 2),
+    ("odd_heights_empty_chip_prep", [(5, 1, False), (0, 2, False), (6, 1, True)], 3, 3, 102, 4, 3, 2, 2),
+    ("four_chips", [(32, 2, True), (96, 1, False), (128, 1, False), (0, 1, True)], 5, 7, 103, 8, 4, 2, 3),
+    ("medium", [(4096, 2, True), (1024 + 32, 3, False), (0, 1, False), (8192, 1, True), (2048, 4, False)], 12, 13, 104, 16, 8, 5, 6),
+]
+
+
+def run_case(name, spec, log_stack, mlr, seed, nq, pw, bpw, gpw):
+    rng = np.random.default_rng(seed)
+    blob, heights, mains, preps, pv = _synth_machine_gkr(rng, spec)
+    names = [f"Chip{i:02d}" for i in range(len(heights))]
+    ch = O.Challenger()
+    ch.observe(O.rand_field(rng, 9))
+    pc, words = O.prove_shard_verify(blob, heights, mains, preps, names, pv, log_stack, mlr, ch, num_queries=nq, pow_bits=pw,
+                                     batch_pow_bits=bpw, gkr_pow_bits=gpw)
+    n_sec = int(words[0])
+    lens = [int(x) for x in words[1:1 + n_sec]]
+    off = 1 + n_sec
+    heads = []
+    for ln in lens:
+        sec = words[off:off + ln]
+        heads.append({"first": [int(x) for x in sec[:8]], "last": [int(x) for x in sec[-8:]]})
+        off += ln
+    return {
+        "name": name, "spec": [list(s) for s in spec], "log_stacking_height": log_stack, "max_log_row_count": mlr, "seed": seed,
+        "num_queries": nq, "pow_bits": pw, "batch_pow_bits": bpw, "gkr_pow_bits": gpw,
+        "prep_commit": [int(x) for x in pc], "main_commit": [int(x) for x in words[1 + n_sec:1 + n_sec + 8]],
+        "final_challenger": [int(x) for x in ch.st], "section_lengths": lens, "n_words": int(words.size),
+        "sha256": hashlib.sha256(words.astype("<u4").tobytes()).hexdigest(), "sections": heads,
+    }
+
+
+def main():
+    out = {"generator": "tools/gen_golden_proofs.py (oracle/liboracle.so; minimum-witness grinding)",
+           "format": "proof words = [n_sections][lengths] then main commitment | LogUp-GKR | zerocheck + opened values | evaluation proof | "
+                     "public values; u32 little-endian for the hash",
+           "cases": [run_case(*c) for c in CASES]}
+    path = os.path.join(ROOT, "tests", "golden", "shard_proofs.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", path, [c["sha256"][:12] for c in out["cases"]])
+
+
+if __name__ == "__main__":
+    main()

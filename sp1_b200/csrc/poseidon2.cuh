@@ -129,15 +129,17 @@ KB_HD void int_layer_lazy(uint32_t (&s)[16]) {
     s[0] = y0;
 }
 
+// Loop shapes measured with tools/p2_bench.cu on a B200: full rounds unrolled x2 and partial rounds x4 give 4.61 Gperm/s,
+// rolled loops 4.50, fully unrolled code 4.01 (instruction cache).
 KB_HD void permute(uint32_t (&s)[16]) {
     ext_layer(s);
-#pragma unroll 1
+#pragma unroll 2
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < 16; i++) s[i] = sbox(s[i], P2_RC.ext[r * 16 + i]);
         ext_layer(s);
     }
-#pragma unroll 1
+#pragma unroll 4
     for (int r = 0; r < 20; r++) {
         s[0] = sbox(s[0], P2_RC.inr[r]);
         int_layer_lazy(s);
@@ -145,7 +147,7 @@ KB_HD void permute(uint32_t (&s)[16]) {
     // lanes 1..15 back to canonical (< 2p + 2^15 < 3p)
 #pragma unroll
     for (int i = 1; i < 16; i++) { uint32_t v = s[i]; v = umin(v, v - kb::P); s[i] = umin(v, v - kb::P); }
-#pragma unroll 1
+#pragma unroll 2
     for (int r = 4; r < 8; r++) {
 #pragma unroll
         for (int i = 0; i < 16; i++) s[i] = sbox(s[i], P2_RC.ext[r * 16 + i]);

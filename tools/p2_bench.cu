@@ -83,6 +83,31 @@ __device__ __forceinline__ void permute(uint32_t (&s)[16]) {
 }
 }  // namespace v
 
+// partial / full round loops with explicit unroll factors (the product uses "#pragma unroll 1" for both)
+#define P2_UNROLL_VARIANT(NAME, UP, UF)                                                                         \
+    __device__ __forceinline__ void NAME(uint32_t (&s)[16]) {                                                   \
+        p2::ext_layer(s);                                                                                       \
+        _Pragma(UF) for (int r = 0; r < 4; r++) {                                                               \
+            _Pragma("unroll") for (int i = 0; i < 16; i++) s[i] = p2::sbox(s[i], p2::RC.ext[r * 16 + i]);       \
+            p2::ext_layer(s);                                                                                   \
+        }                                                                                                       \
+        _Pragma(UP) for (int r = 0; r < 20; r++) { s[0] = p2::sbox(s[0], p2::RC.inr[r]); p2::int_layer_lazy(s); } \
+        _Pragma("unroll") for (int i = 1; i < 16; i++) { uint32_t x = s[i]; x = kb::umin(x, x - kb::P); s[i] = kb::umin(x, x - kb::P); } \
+        _Pragma(UF) for (int r = 4; r < 8; r++) {                                                               \
+            _Pragma("unroll") for (int i = 0; i < 16; i++) s[i] = p2::sbox(s[i], p2::RC.ext[r * 16 + i]);       \
+            p2::ext_layer(s);                                                                                   \
+        }                                                                                                       \
+    }
+namespace u {
+P2_UNROLL_VARIANT(p2f1, "unroll 2", "unroll 1")
+P2_UNROLL_VARIANT(p4f1, "unroll 4", "unroll 1")
+P2_UNROLL_VARIANT(p5f1, "unroll 5", "unroll 1")
+P2_UNROLL_VARIANT(p10f1, "unroll 10", "unroll 1")
+P2_UNROLL_VARIANT(p1f2, "unroll 1", "unroll 2")
+P2_UNROLL_VARIANT(p4f2, "unroll 4", "unroll 2")
+P2_UNROLL_VARIANT(p20f1, "unroll 20", "unroll 1")
+}  // namespace u
+
 template <int V> struct Var;
 template <> struct Var<0> { static constexpr const char* name = "p2::permute (product)"; static __device__ void f(uint32_t (&s)[16]) { p2::permute(s); } };
 template <> struct Var<1> { static constexpr const char* name = "half-product sbox, loops"; static __device__ void f(uint32_t (&s)[16]) { v::permute<0, false>(s); } };
@@ -90,6 +115,14 @@ template <> struct Var<2> { static constexpr const char* name = "wide sbox, loop
 template <> struct Var<3> { static constexpr const char* name = "mixed sbox, loops"; static __device__ void f(uint32_t (&s)[16]) { v::permute<2, false>(s); } };
 template <> struct Var<4> { static constexpr const char* name = "half-product sbox, fully unrolled"; static __device__ void f(uint32_t (&s)[16]) { v::permute<0, true>(s); } };
 template <> struct Var<5> { static constexpr const char* name = "wide sbox, fully unrolled"; static __device__ void f(uint32_t (&s)[16]) { v::permute<1, true>(s); } };
+
+template <> struct Var<6> { static constexpr const char* name = "product sbox, partial x2"; static __device__ void f(uint32_t (&s)[16]) { u::p2f1(s); } };
+template <> struct Var<7> { static constexpr const char* name = "product sbox, partial x4"; static __device__ void f(uint32_t (&s)[16]) { u::p4f1(s); } };
+template <> struct Var<8> { static constexpr const char* name = "product sbox, partial x5"; static __device__ void f(uint32_t (&s)[16]) { u::p5f1(s); } };
+template <> struct Var<9> { static constexpr const char* name = "product sbox, partial x10"; static __device__ void f(uint32_t (&s)[16]) { u::p10f1(s); } };
+template <> struct Var<10> { static constexpr const char* name = "product sbox, full x2"; static __device__ void f(uint32_t (&s)[16]) { u::p1f2(s); } };
+template <> struct Var<11> { static constexpr const char* name = "product sbox, partial x4, full x2"; static __device__ void f(uint32_t (&s)[16]) { u::p4f2(s); } };
+template <> struct Var<12> { static constexpr const char* name = "product sbox, partial x20"; static __device__ void f(uint32_t (&s)[16]) { u::p20f1(s); } };
 
 template <int V>
 __global__ void __launch_bounds__(256) bench(uint32_t* out, int iters) {
@@ -144,5 +177,12 @@ int main() {
     run<3>(d_out, pr.multiProcessorCount);
     run<4>(d_out, pr.multiProcessorCount);
     run<5>(d_out, pr.multiProcessorCount);
+    run<6>(d_out, pr.multiProcessorCount);
+    run<7>(d_out, pr.multiProcessorCount);
+    run<8>(d_out, pr.multiProcessorCount);
+    run<9>(d_out, pr.multiProcessorCount);
+    run<10>(d_out, pr.multiProcessorCount);
+    run<11>(d_out, pr.multiProcessorCount);
+    run<12>(d_out, pr.multiProcessorCount);
     return 0;
 }

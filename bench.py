@@ -90,6 +90,10 @@ def cpu_baseline(workload_name, target_seconds=20.0):
     from tests import oracle_lib as O
     from sp1_b200 import synth_air as SA
     L = O.lib()
+    try:  # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)
+        L.orc_set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
     cores = L.orc_num_threads()
     full = W.synthetic_machine(workload_name, seed=42)
     scale = (1 << 22) / W.area_of(full["main_shapes"])

@@ -88,6 +88,14 @@ int orc_num_threads() {
     return 1;
 #endif
 }
+// launchers such as torchrun export OMP_NUM_THREADS=1: the CPU baseline arm asks for the host's cores explicitly
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 // ---- field -------------------------------------------------------------------------------------
 uint32_t orc_to_monty(uint32_t canonical) { return F::from_canonical(canonical).v; }

@@ -55,6 +55,35 @@ __global__ void __launch_bounds__(256) leaf_hash_kernel(const uint32_t* __restri
     store_digest(digests + i * 8, s);
 }
 
+// parents[j] = compress(children[2j], children[2j+1]): one thread per parent, full occupancy (32 registers) — used for the wide
+// layers of a tree, where throughput matters; the narrow top goes through merkle_subtree_kernel (fewer launches)
+__global__ void __launch_bounds__(256) compress_layer_kernel(const uint32_t* __restrict__ children, uint32_t* __restrict__ parents,
+                                                             uint64_t n_parents) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_parents) return;
+    uint32_t s[16];
+    const uint4* p = reinterpret_cast<const uint4*>(children + j * 16);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { uint4 v = __ldg(p + k); s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w; }
+    p2::permute(s);
+    store_digest(parents + j * 8, s);
+}
+// FRI-round leaves: leaf i = hash(cw[2i] limbs, cw[2i+1] limbs) -- one permutation (8 words = rate), limb-major codeword of length m
+__global__ void __launch_bounds__(256) fri_leaf_hash_kernel(const uint32_t* __restrict__ cw, uint64_t m, uint32_t* __restrict__ digests) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m / 2) return;
+    uint32_t s[16];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        const uint2 v = *reinterpret_cast<const uint2*>(cw + l * m + 2 * i);
+        s[l] = v.x; s[4 + l] = v.y;
+    }
+#pragma unroll
+    for (int k = 8; k < 16; k++) s[k] = 0;
+    p2::permute(s);
+    store_digest(digests + i * 8, s);
+}
+
 // ---- subtree kernel: up to 9 compress levels per launch ------------------------------------------------------------------------
 // A block takes 512 consecutive digests of layer k0 (or, MODE 1, the 512 FRI leaves it first hashes from the limb-major
 // codeword: leaf i = hash(cw[2i] limbs, cw[2i+1] limbs), one permutation) and climbs: level j halves the active threads, parents
@@ -190,17 +219,33 @@ sp1b200_err sp1b200_merkle_commit_device(sp1b200_ctx* ctx, const uint32_t* d_mat
 
 
 // climbs from layer 0 (MODE 0: already filled; MODE 1: FRI leaves hashed from the codeword `src` of length m) to the root
+// Layers with more than 2^SUBTREE_LOG nodes go through the flat one-thread-per-node kernels (full occupancy: the fused subtree
+// kernel reaches 2.7 Gperm/s on a 2^22-leaf tree against 4.4 for the flat ones, profiles/launches_r01_final_S2.txt); the narrow
+// top of every tree, where launch count and not throughput matters, is climbed by the subtree kernel.
+constexpr uint32_t SUBTREE_LOG = 16;
 template <int MODE>
 static sp1b200_err build_tree(sp1b200_ctx* ctx, const uint32_t* src, uint64_t m, uint32_t* d_layers, uint32_t log_h, uint32_t width,
                               uint32_t* d_root_commit16, Mail mail) {
+    const uint64_t h = (uint64_t)1 << log_h;
+    auto layer_ptr = [&](uint32_t k) { return d_layers + (2 * h - (2 * h >> k)) * 8; };
     uint32_t k0 = 0;
+    bool leaves_done = (MODE == 0);
+    if (MODE == 1 && log_h > SUBTREE_LOG) {
+        SP1_LAUNCH(ctx, fri_leaf_hash_kernel, (unsigned)((h + 255) / 256), 256, 0, src, m, d_layers);
+        leaves_done = true;
+    }
+    while (leaves_done && log_h - k0 > SUBTREE_LOG) {
+        const uint64_t n_par = h >> (k0 + 1);
+        SP1_LAUNCH(ctx, compress_layer_kernel, (unsigned)((n_par + 255) / 256), 256, 0, layer_ptr(k0), layer_ptr(k0 + 1), n_par);
+        k0++;
+    }
     while (k0 < log_h) {
         const uint32_t L = log_h - k0 < 9 ? log_h - k0 : 9;
         const uint64_t n_children = (uint64_t)1 << (log_h - k0);
         const unsigned blocks = (unsigned)(n_children > 512 ? n_children / 512 : 1);
         const int fin = (k0 + L == log_h);
         const Mail none{nullptr, nullptr, 0};
-        if (MODE == 1 && k0 == 0) SP1_LAUNCH(ctx, merkle_subtree_kernel<1>, blocks, 256, 0, src, m, d_layers, log_h, k0, L, fin, width, d_root_commit16, fin ? mail : none);
+        if (!leaves_done && k0 == 0) SP1_LAUNCH(ctx, merkle_subtree_kernel<1>, blocks, 256, 0, src, m, d_layers, log_h, k0, L, fin, width, d_root_commit16, fin ? mail : none);
         else SP1_LAUNCH(ctx, merkle_subtree_kernel<0>, blocks, 256, 0, nullptr, (uint64_t)0, d_layers, log_h, k0, L, fin, width, d_root_commit16, fin ? mail : none);
         k0 += L;
     }

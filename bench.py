@@ -4,7 +4,7 @@
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
   python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
 
-A "step" proves one batch of `--inflight` synthetic shards per GPU (default 3, each on its own library context + CUDA stream +
+A "step" proves one batch of `--inflight` synthetic shards per GPU (default 5 for S2, each on its own library context + CUDA stream +
 host transcript thread, so that the latency-bound sumcheck tails of one shard overlap the NTT / Poseidon2 kernels of another);
 a shard = workload S2 by default (~1.9e8 trace cells = 2^22 cycles at 45 cells/cycle): main-trace jagged commit (RS-encode NTT +
 Poseidon2 Merkle) followed by the phases listed in config.phases.  Per-phase times and the roofline lines are taken from a
@@ -90,8 +90,16 @@ def cpu_baseline(workload_name, target_seconds=20.0):
     from tests import oracle_lib as O
     from sp1_b200 import synth_air as SA
     L = O.lib()
-    try:  # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)
-        L.orc_set_num_threads(len(os.sched_getaffinity(0)))
+    # one OpenMP thread per physical core this process may use: launchers such as torchrun export OMP_NUM_THREADS=1, and two
+    # threads per core (SMT) measured 5x slower on the oracle's barrier-heavy loops (1.2 k vs 6.5 k cycles/s on the GPU box)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+        try:
+            sib = open("/sys/devices/system/cpu/cpu0/topology/thread_siblings_list").read().strip()
+            smt = 2 if ("," in sib or "-" in sib) else 1
+        except OSError:
+            smt = 1
+        L.orc_set_num_threads(max(1, ncpu // smt))
     except (AttributeError, OSError):
         pass
     cores = L.orc_num_threads()
@@ -145,7 +153,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="S2", choices=list(W.WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=3,
+    ap.add_argument("--inflight", type=int, default=0,
                     help="shards proven concurrently per GPU (one library context + stream + host thread each): the latency-bound "
                          "sumcheck tails of one shard overlap the NTT / Poseidon2 kernels of another")
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "serial"],
@@ -198,6 +206,10 @@ def main():
     prep_rows = [h for h, _, wp in specs if wp]
     _, h_prep = lib.jagged_commit_dense(d_prep, prep_rows, [1] * len(prep_rows))
     # further in-flight provers on the same GPU: own context (stream, mailbox, upload slots), own machine / preprocessed commit
+    # default: as many shards in flight as the device memory comfortably holds (measured: ~24 GB per S2 context at the pool's high
+    # water mark; throughput saturates at 5-6 contexts), never more than 5
+    if args.inflight <= 0:
+        args.inflight = {"S1": 5, "S2": 5, "S3": 3}.get(args.workload, 3)
     provers = [(lib, machine, h_prep)]
     for _ in range(1, args.inflight):
         l2 = Lib(device=local)
@@ -335,6 +347,7 @@ def main():
                                "note": "algorithmic 20 B/cell (4 B read + 16 B codeword write); integer-pipe bound (46 modular products per cell), see DESIGN.md"},
         "kernels_ms_per_shard_alone": phases,
         "inflight": len(provers), "ms_per_shard": ms_dev / args.steps / len(provers),
+        "gpu_mem_used_gb": round((torch.cuda.mem_get_info(dev)[1] - torch.cuda.mem_get_info(dev)[0]) / 2**30, 1),
         "poseidon2": {"leaf+compress_perms_per_step": int(perms), "gperm_per_s": perms / (merkle_ms / 1e3) / 1e9,
                       "note": "INT32-ALU bound (see DESIGN.md), not HBM bound"},
     }

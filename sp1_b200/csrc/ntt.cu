@@ -111,6 +111,8 @@ __global__ void rs_step_b_generic(uint32_t* __restrict__ buf, int L1, int L2, in
 // ==== fast path: radix-8 butterflies in registers, 2-3 shared-memory exchanges per transform =================
 
 // (a - c) * w with the difference left unreduced in (0, 2p): valid Montgomery operand since w < p
+// (measured alternatives, 16 columns of 2^21: this subtractive Montgomery form 1.253 ms; additive wide form 1.337 ms; Shoup
+// twiddles slower still — DESIGN.md 3.1)
 __device__ __forceinline__ uint32_t submul(uint32_t a, uint32_t c, uint32_t w) { return kb::mul(a - c + kb::P, w); }
 
 // in-place radix-8 decimation-in-frequency butterfly on v[0..8) (v[j], j bit 2 = most significant of the 3 index bits)

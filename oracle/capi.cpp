@@ -492,4 +492,174 @@ int64_t orc_prove_shard_verify(const uint32_t* machine_blob, const uint64_t* hei
     return (int64_t)o.size();
 }
 
+
+// ---- verify-only: the restated ShardVerifier::verify_shard (crates/hypercube/src/verifier/shard.rs:437-750) on proof WORDS produced
+// elsewhere (the CUDA library).  No trace data is needed: shapes come from the machine blob and the heights.  Returns 0 if the proof
+// is accepted, -1 if rejected (reason on stderr), -2 if the words do not parse.  challenger_state: the state the prover started from
+// (updated to the verifier's final state, which must equal the prover's).
+namespace {
+struct WordReader {
+    const uint32_t* p; const uint32_t* end; bool ok = true;
+    uint32_t u() { if (p >= end) { ok = false; return 0; } return *p++; }
+    F f() { return F::raw(u()); }
+    EF ef() { EF e; for (int i = 0; i < 4; i++) e.c[i] = f(); return e; }
+    Digest dg() { Digest d; for (int i = 0; i < 8; i++) d.d[i] = f(); return d; }
+};
+PartialSumcheckProof get_sumcheck(WordReader& r) {
+    PartialSumcheckProof p;
+    const uint32_t n = r.u();
+    if (n > 4096) { r.ok = false; return p; }
+    p.polys.resize(n);
+    for (auto& u : p.polys) { const uint32_t m = r.u(); if (m > 64) { r.ok = false; return p; } u.c.resize(m); for (auto& c : u.c) c = r.ef(); }
+    p.claimed_sum = r.ef();
+    p.point.resize(n);
+    for (auto& x : p.point) x = r.ef();
+    p.eval = r.ef();
+    return p;
+}
+OpeningAndProof get_opening(WordReader& r, size_t nq, size_t width, unsigned log_height) {
+    OpeningAndProof op;
+    op.values.resize(nq * width);
+    for (auto& v : op.values) v = r.f();
+    op.proof.merkle_root = r.dg();
+    op.proof.log_tensor_height = r.u();
+    op.proof.width = r.u();
+    if (op.proof.log_tensor_height != log_height || op.proof.width != width) r.ok = false;
+    op.proof.paths.resize(nq * log_height);
+    for (auto& d : op.proof.paths) d = r.dg();
+    return op;
+}
+}  // namespace
+
+int64_t orc_verify_shard(const uint32_t* machine_blob, const uint64_t* heights, const char* names, uint32_t log_stack, uint32_t max_log_rows,
+                         uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits, uint32_t batch_pow_bits, uint32_t gkr_pow_bits,
+                         uint32_t* challenger_state, const uint32_t* prep_commit8, const uint32_t* words, uint64_t n_words) {
+    FriParams fp; fp.log_blowup = log_blowup; fp.num_queries = num_queries; fp.pow_bits = pow_bits; fp.batch_pow_bits = batch_pow_bits;
+    const uint32_t* rest;
+    std::vector<MachineChip> mc = parse_machine(machine_blob, &rest);
+    auto inter = parse_interactions(rest, mc.size());
+    const size_t n = mc.size();
+    std::vector<std::string> nm;
+    { const char* p = names; for (size_t k = 0; k < n; k++) { nm.emplace_back(p); p += nm.back().size() + 1; } }
+    std::vector<GkrChip> gchips(n);
+    std::vector<ZcChip> zchips(n);
+    uint64_t prep_area = 0, main_area = 0;
+    bool has_prep = false;
+    for (size_t k = 0; k < n; k++) {
+        gchips[k].height = heights[k]; gchips[k].main_w = mc[k].main_w; gchips[k].prep_w = mc[k].prep_w; gchips[k].inter = inter[k];
+        zchips[k].air = &mc[k].air; zchips[k].height = heights[k]; zchips[k].main_w = mc[k].main_w; zchips[k].prep_w = mc[k].prep_w;
+        main_area += heights[k] * mc[k].main_w;
+        if (mc[k].prep_w) { has_prep = true; prep_area += heights[k] * mc[k].prep_w; }
+    }
+    if (n_words < 6 || words[0] != 5) return -2;
+    const uint64_t l0 = words[1], l1 = words[2], l2 = words[3], l3 = words[4], l4 = words[5];
+    if (6 + l0 + l1 + l2 + l3 + l4 != n_words || l0 != 8) return -2;
+    const uint32_t* s0 = words + 6; const uint32_t* s1 = s0 + l0; const uint32_t* s2 = s1 + l1; const uint32_t* s3 = s2 + l2; const uint32_t* s4 = s3 + l3;
+    Digest main_commit; for (int i = 0; i < 8; i++) main_commit.d[i] = F::raw(s0[i]);
+    std::vector<F> pv(l4);
+    for (uint64_t i = 0; i < l4; i++) pv[i] = F::raw(s4[i]);
+    // LogUp-GKR section
+    GkrProof gp;
+    {
+        WordReader r{s1, s2};
+        const uint32_t n_out = r.u();
+        if (n_out > (1u << 20)) return -2;
+        gp.out_num.resize(n_out); gp.out_den.resize(n_out);
+        for (auto& e : gp.out_num) e = r.ef();
+        for (auto& e : gp.out_den) e = r.ef();
+        const uint32_t nr = r.u();
+        if (nr > 64) return -2;
+        gp.rounds.resize(nr);
+        for (auto& q : gp.rounds) { q.n0 = r.ef(); q.n1 = r.ef(); q.d0 = r.ef(); q.d1 = r.ef(); q.sc = get_sumcheck(r); }
+        gp.point.resize(max_log_rows);
+        for (auto& e : gp.point) e = r.ef();
+        gp.main_open.resize(n); gp.prep_open.resize(n);
+        for (size_t k = 0; k < n; k++) {
+            gp.main_open[k].resize(mc[k].main_w); gp.prep_open[k].resize(mc[k].prep_w);
+            for (auto& e : gp.main_open[k]) e = r.ef();
+            for (auto& e : gp.prep_open[k]) e = r.ef();
+        }
+        gp.witness = r.f();
+        if (!r.ok || r.p != s2) return -2;
+    }
+    // zerocheck section
+    ZerocheckResult zr;
+    {
+        WordReader r{s2, s3};
+        zr.proof = get_sumcheck(r);
+        zr.opened.resize(n);
+        for (size_t k = 0; k < n; k++) {
+            zr.opened[k].prep.resize(mc[k].prep_w); zr.opened[k].main.resize(mc[k].main_w);
+            for (auto& e : zr.opened[k].prep) e = r.ef();
+            for (auto& e : zr.opened[k].main) e = r.ef();
+            zr.opened[k].degree = point_from_usize(heights[k], max_log_rows + 1);
+        }
+        if (!r.ok || r.p != s3) return -2;
+    }
+    // evaluation proof section
+    JaggedProof jp;
+    const size_t n_rounds = has_prep ? 2 : 1;
+    {
+        WordReader r{s3, s4};
+        const uint64_t S = (uint64_t)1 << log_stack;
+        std::vector<size_t> ncols;
+        if (has_prep) ncols.push_back((size_t)std::max<uint64_t>((prep_area + S - 1) / S, 1));
+        ncols.push_back((size_t)std::max<uint64_t>((main_area + S - 1) / S, 1));
+        BasefoldProof& bf = jp.pcs.basefold;
+        bf.univariate_messages.resize(log_stack);
+        for (auto& m : bf.univariate_messages) { m[0] = r.ef(); m[1] = r.ef(); }
+        bf.fri_commitments.resize(log_stack);
+        for (auto& d : bf.fri_commitments) d = r.dg();
+        for (size_t q = 0; q < n_rounds; q++) bf.component.push_back(get_opening(r, num_queries, ncols[q], log_stack + log_blowup));
+        for (uint32_t q = 0; q < log_stack; q++) bf.query_phase.push_back(get_opening(r, num_queries, 8, log_stack + log_blowup - q - 1));
+        bf.final_poly = r.ef();
+        bf.pow_witness = r.f();
+        bf.batch_grinding_witness = r.f();
+        jp.pcs.batch_evaluations.resize(n_rounds);
+        for (size_t q = 0; q < n_rounds; q++) { jp.pcs.batch_evaluations[q].resize(ncols[q]); for (auto& e : jp.pcs.batch_evaluations[q]) e = r.ef(); }
+        jp.sumcheck = get_sumcheck(r);
+        jp.jagged_eval = get_sumcheck(r);
+        jp.rc_cc.resize(n_rounds);
+        for (auto& v : jp.rc_cc) {
+            const uint32_t cnt = r.u();
+            if (cnt > 4096) return -2;
+            v.resize(cnt);
+            for (auto& rc : v) { rc.first = r.u(); rc.second = r.u(); }
+        }
+        jp.merkle_commits.resize(n_rounds);
+        for (auto& d : jp.merkle_commits) d = r.dg();
+        jp.expected_eval = r.ef();
+        jp.max_log_rows = r.u();
+        jp.log_m = r.u();
+        if (!r.ok || r.p != s4) return -2;
+    }
+    // ---- verify_shard order (same as the verify block of orc_prove_shard_verify)
+    Challenger vch; chal_load(vch, challenger_state);
+    vch.observe_slice(pv.data(), pv.size());
+    vch.observe(main_commit);
+    vch.observe(F::from_canonical(n));
+    for (size_t k = 0; k < n; k++) {
+        vch.observe(F::from_canonical(heights[k])); vch.observe(F::from_canonical(nm[k].size()));
+        for (unsigned char b : nm[k]) vch.observe(F::from_canonical(b));
+    }
+    const char* err = gkr_verify(gchips, max_log_rows, gkr_pow_bits, gp, vch);
+    if (!err) err = zerocheck_verify(zchips, zr.opened, gp.point, gp.main_open, gp.prep_open, zr.proof, pv, max_log_rows, vch);
+    if (!err) {
+        std::vector<Digest> commits;
+        std::vector<std::vector<EF>> jclaims;
+        if (has_prep) {
+            Digest pc; for (int i = 0; i < 8; i++) pc.d[i] = F::raw(prep_commit8[i]);
+            commits.push_back(pc);
+            std::vector<EF> c; for (auto& o : zr.opened) c.insert(c.end(), o.prep.begin(), o.prep.end());
+            jclaims.push_back(c);
+        }
+        commits.push_back(main_commit);
+        { std::vector<EF> c; for (auto& o : zr.opened) c.insert(c.end(), o.main.begin(), o.main.end()); jclaims.push_back(c); }
+        err = jagged_verify(commits, zr.proof.point, jclaims, jp, vch, log_stack, max_log_rows, fp);
+    }
+    if (err) { std::fprintf(stderr, "restated shard verifier rejected the proof: %s\n", err); return -1; }
+    chal_store(vch, challenger_state);
+    return 0;
+}
+
 }  // extern "C"

@@ -287,3 +287,20 @@ def prove_shard_verify(blob, heights, mains, preps, names, pv, log_stack, max_lo
     if nw < 0:
         raise RuntimeError(f"oracle prove_shard failed ({nw})")
     return pc, out[:nw].copy()
+
+
+def verify_shard(blob, heights, names, log_stack, max_log_rows, challenger, prep_commit, words, log_blowup=2, num_queries=124, pow_bits=16,
+                 batch_pow_bits=5, gkr_pow_bits=12):
+    """Verify-only: the restated ShardVerifier::verify_shard on proof words produced elsewhere (e.g. by the CUDA library).
+    `challenger`: the state the prover started from; updated to the verifier's final state.  Returns 0 (accepted), -1 (rejected),
+    -2 (the words do not parse)."""
+    H = (C.c_uint64 * len(heights))(*heights)
+    nm = b"".join(n.encode() + b"\0" for n in names)
+    blob = np.ascontiguousarray(blob, dtype=np.uint32)
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    pc = np.ascontiguousarray(prep_commit if prep_commit is not None else np.zeros(8), dtype=np.uint32)
+    f = lib().orc_verify_shard
+    f.restype = C.c_int64
+    return int(f(ptr(blob), H, C.c_char_p(nm), C.c_uint32(log_stack), C.c_uint32(max_log_rows), C.c_uint32(log_blowup), C.c_uint32(num_queries),
+                 C.c_uint32(pow_bits), C.c_uint32(batch_pow_bits), C.c_uint32(gkr_pow_bits), ptr(challenger.st), ptr(pc), ptr(words),
+                 C.c_uint64(words.size)))

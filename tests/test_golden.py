@@ -12,3 +12,26 @@ def test_oracle_reproduces_golden_shard_proofs(case):
                                      num_queries=case["num_queries"], pow_bits=case["pow_bits"], batch_pow_bits=case["batch_pow_bits"],
                                      gkr_pow_bits=case["gkr_pow_bits"])
     G.check_words(case, pc, words, ch.st)
+
+
+@pytest.mark.parametrize("case", G.cases(), ids=lambda c: c["name"])
+def test_verify_only_accepts_oracle_proofs_and_rejects_tampering(case):
+    """orc_verify_shard (verifier alone, from the proof WORDS) accepts what the prover wrote, ends in the prover's challenger
+    state, and rejects a flipped word in every section"""
+    import numpy as np
+    blob, heights, mains, preps, pv, names, ch = G.inputs_of(case)
+    start = ch.clone()
+    kw = dict(num_queries=case["num_queries"], pow_bits=case["pow_bits"], batch_pow_bits=case["batch_pow_bits"], gkr_pow_bits=case["gkr_pow_bits"])
+    pc, words = O.prove_shard_verify(blob, heights, mains, preps, names, pv, case["log_stacking_height"], case["max_log_row_count"], ch, **kw)
+    v = start.clone()
+    assert O.verify_shard(blob, heights, names, case["log_stacking_height"], case["max_log_row_count"], v, pc, words, **kw) == 0
+    assert (v.st == ch.st).all()
+    n_sec = int(words[0])
+    off = 1 + n_sec
+    for ln in [int(x) for x in words[1:1 + n_sec]]:
+        bad = words.copy()
+        bad[off + ln // 2] ^= 1
+        v = start.clone()
+        assert O.verify_shard(blob, heights, names, case["log_stacking_height"], case["max_log_row_count"], v, pc, bad, **kw) != 0
+        off += ln
+    assert O.verify_shard(blob, heights, names, case["log_stacking_height"], case["max_log_row_count"], start.clone(), pc, words[:-1], **kw) == -2

@@ -1,0 +1,58 @@
+"""Full-size parity property (BASELINE.json's sha-bench-like shard, workload S2: 198.5 M trace cells, 35 chips up to 2^22 rows, core
+protocol parameters: stacking height 2^21, 124 queries, 16 + 5 + 12 proof-of-work bits): the oracle cannot PROVE this size in test
+time, but the restated reference verifier (ShardVerifier::verify_shard, run by the oracle from the proof words alone) must accept the
+proof the CUDA library produces, end in the prover's challenger state, and reject it after a one-bit change."""
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("workload", ["S1", "S2"])
+def test_full_size_gpu_proof_is_accepted_by_the_restated_reference_verifier(workload):
+    import torch
+    from sp1_b200 import Lib
+    from sp1_b200 import synth_air as SA
+    from sp1_b200 import workload as W
+    from sp1_b200.lib import HostChallenger
+
+    dev = torch.device("cuda", 0)
+    mach = W.synthetic_machine(workload, seed=42)
+    specs, names = mach["specs"], mach["names"]
+    heights = [h for h, _, _ in specs]
+    pv0 = 12345
+    pv = O.to_monty(np.array([pv0, 5, 6, 7]))
+    mains, preps = [], []
+    for i, (h, g, wp) in enumerate(specs):
+        m_, p_ = SA.synth_trace_cuda(h, g, wp, pv0, 7000 + i, dev)
+        mains.append(m_)
+        if wp:
+            preps.append(p_)
+    d_main = torch.cat(mains).contiguous()
+    d_prep = torch.cat(preps).contiguous()
+    del mains, preps
+    lib = Lib(device=0)                                   # core parameters (sp1b200_default_core_params)
+    machine = lib.machine_create(mach["blob"])
+    prep_rows = [h for h, _, wp in specs if wp]
+    pc, h_prep = lib.jagged_commit_dense(d_prep, prep_rows, [1] * len(prep_rows))
+    st0 = HostChallenger().st.copy()
+    st = st0.copy()
+    words = lib.prove_shard(machine, h_prep, d_main, heights, names, pv, st)
+    again = lib.prove_shard(machine, h_prep, d_main, heights, names, pv, st0.copy())
+    assert (words == again).all(), "the proof is not deterministic"
+    lib.jagged_round_free(h_prep)
+    lib.machine_free(machine)
+    lib.close()
+    del d_main, d_prep
+    torch.cuda.empty_cache()
+
+    v = O.Challenger(); v.st[:] = st0
+    assert O.verify_shard(mach["blob"], heights, names, 21, 22, v, pc, words) == 0, "restated reference verifier rejected the GPU proof"
+    assert (v.st == st).all(), "verifier and prover end in different challenger states"
+    n_sec = int(words[0])
+    off = 1 + n_sec + int(words[1]) + int(words[2]) // 2      # a word in the middle of the LogUp-GKR section
+    bad = words.copy(); bad[off] ^= 1
+    v2 = O.Challenger(); v2.st[:] = st0
+    assert O.verify_shard(mach["blob"], heights, names, 21, 22, v2, pc, bad) != 0

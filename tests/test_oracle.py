@@ -327,3 +327,35 @@ def test_whole_shard_roundtrip(spec, log_stack, mlr):
     pc, words = O.prove_shard_verify(blob, heights, mains, preps, names, pv, log_stack, mlr, c1, num_queries=8, pow_bits=4,
                                      batch_pow_bits=2, gkr_pow_bits=3)
     assert words[0] == 5 and words.size == 6 + int(words[1:6].sum())
+
+
+def _synth_machine_gkr_custom(rng, spec, no_interactions=(), pv0=12345):
+    """like _synth_machine_gkr, but the chips listed in `no_interactions` carry no LogUp interactions at all"""
+    from sp1_b200 import synth_air as SA
+    words, iwords, mains, preps, heights = [], [], [], [], []
+    for k, (h, g, wp) in enumerate(spec):
+        w, _, _ = SA.synth_chip(g, wp)
+        words.append(w); iwords.append([0] if k in no_interactions else SA.synth_interactions(g, wp))
+        m, p = SA.synth_trace(rng, h, g, wp, pv0)
+        mains.append(m); preps.append(p); heights.append(h)
+    pv = O.to_monty(np.array([pv0, 5, 6, 7]))
+    return SA.machine_blob_with_interactions(words, iwords), heights, mains, preps, pv
+
+
+GKR_EDGE_CASES = [
+    # spec, chips without interactions, max_log_rows
+    ([(64, 1, False), (32, 2, False), (16, 1, True)], (1,), 7),       # a chip with constraints but no interactions
+    ([(2, 1, False), (1, 1, False)], (0,), 3),                          # 4 interactions in all, heights 2 and 1
+    ([(8, 3, False), (0, 1, False), (8, 1, True)], (2,), 4),            # absent chip + silent chip with preprocessed columns
+]
+
+
+@pytest.mark.parametrize("spec,silent,mlr", GKR_EDGE_CASES)
+def test_logup_gkr_roundtrip_with_silent_chips(spec, silent, mlr):
+    rng = np.random.default_rng(53)
+    blob, heights, mains, preps, pv = _synth_machine_gkr_custom(rng, spec, silent)
+    ch = O.Challenger(); ch.observe(O.rand_field(rng, 4))
+    c1 = ch.clone()
+    words = O.gkr_prove_verify(blob, heights, mains, preps, mlr, c1, gkr_pow_bits=4)
+    c2 = ch.clone()
+    assert (O.gkr_prove_verify(blob, heights, mains, preps, mlr, c2, gkr_pow_bits=4) == words).all()

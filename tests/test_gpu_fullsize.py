@@ -1,4 +1,4 @@
-"""Full-size parity property (BASELINE.json's sha-bench-like shard, workload S2: 198.5 M trace cells, 35 chips up to 2^22 rows, core
+"""Full-size parity property (BASELINE.json's sha-bench-like shard, workloads S1, S2 = 198.5 M trace cells and S3 = the full 402 M-cell shard, 35 chips up to 2^22 rows, core
 protocol parameters: stacking height 2^21, 124 queries, 16 + 5 + 12 proof-of-work bits): the oracle cannot PROVE this size in test
 time, but the restated reference verifier (ShardVerifier::verify_shard, run by the oracle from the proof words alone) must accept the
 proof the CUDA library produces, end in the prover's challenger state, and reject it after a one-bit change."""
@@ -10,7 +10,7 @@ from tests import oracle_lib as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("workload", ["S1", "S2"])
+@pytest.mark.parametrize("workload", ["S1", "S2", "S3"])
 def test_full_size_gpu_proof_is_accepted_by_the_restated_reference_verifier(workload):
     import torch
     from sp1_b200 import Lib

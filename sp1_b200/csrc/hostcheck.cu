@@ -36,7 +36,7 @@ void sp1b200_hostcheck_field(const uint32_t* a, const uint32_t* b, uint32_t* add
 // Evaluate ONE chip's constraint program on one row (base-field values) two ways: the bytecode as given, and the stream
 // produced by zc_lower (what the zerocheck kernels interpret).  chip = the per-chip words of the machine blob
 // (sp1b200_machine_create).  out[0..4) = sum_k alpha_pows[assert_alphas[k]] * value_k (original), out[4..8) = lowered;
-// returns the lowered register pressure, or -1 on a lowering error.
+// out[8..12) = the sum over the self-contained pieces; returns the lowered register pressure, or -1 on a lowering error.
 int sp1b200_hostcheck_zc_lower(const uint32_t* chip, const uint32_t* main_row, const uint32_t* prep_row, const uint32_t* pv,
                                const uint32_t* alpha_pows, uint32_t window, uint32_t* out, uint32_t* n_lowered) {
     using hf::E4;
@@ -69,23 +69,39 @@ int sp1b200_hostcheck_zc_lower(const uint32_t* chip, const uint32_t* main_row, c
         for (size_t k = 0; k < hp.assert_regs.size(); k++) acc = acc + E4::load(alpha_pows + 4 * hp.assert_alphas[k]) * regs[hp.assert_regs[k]];
         acc.store(out);
     }
+    auto run = [&](const ZcLowered& Lw) {
+        std::vector<uint32_t> rf(Lw.n_regs, 0);
+        E4 a;
+        for (const ZcInstr& in : Lw.instrs) {
+            switch (in.op) {
+                case ZC_LOAD_MAIN: rf[in.out] = main_row[(uint32_t)in.a | ((uint32_t)in.b << 16)]; break;
+                case ZC_LOAD_PREP: rf[in.out] = prep_row[(uint32_t)in.a | ((uint32_t)in.b << 16)]; break;
+                case ZC_CONST: rf[in.out] = hp.consts[in.a]; break;
+                case ZC_PUBLIC: rf[in.out] = pv[hp.publics[in.a]]; break;
+                case ZC_ADD: { uint32_t x = rf[in.a], y = rf[in.b]; rf[in.out] = hf::add(x, y); break; }
+                case ZC_SUB: { uint32_t x = rf[in.a], y = rf[in.b]; rf[in.out] = hf::sub(x, y); break; }
+                case ZC_MUL: { uint32_t x = rf[in.a], y = rf[in.b]; rf[in.out] = hf::mul(x, y); break; }
+                case ZC_NEG: rf[in.out] = hf::neg(rf[in.a]); break;
+                case ZC_ASSERT: a = a + E4::load(alpha_pows + 4 * in.b) * rf[in.a]; break;
+            }
+        }
+        return a;
+    };
     ZcLowered L = zc_lower(hp, window);
     if (!L.error.empty()) return -1;
     if (n_lowered) *n_lowered = (uint32_t)L.instrs.size();
-    std::vector<uint32_t> rf(L.n_regs, 0);
-    E4 acc;
-    for (const ZcInstr& in : L.instrs) {
-        switch (in.op) {
-            case ZC_LOAD_MAIN: rf[in.out] = main_row[(uint32_t)in.a | ((uint32_t)in.b << 16)]; break;
-            case ZC_LOAD_PREP: rf[in.out] = prep_row[(uint32_t)in.a | ((uint32_t)in.b << 16)]; break;
-            case ZC_CONST: rf[in.out] = hp.consts[in.a]; break;
-            case ZC_PUBLIC: rf[in.out] = pv[hp.publics[in.a]]; break;
-            case ZC_ADD: { uint32_t x = rf[in.a], y = rf[in.b]; rf[in.out] = hf::add(x, y); break; }
-            case ZC_SUB: { uint32_t x = rf[in.a], y = rf[in.b]; rf[in.out] = hf::sub(x, y); break; }
-            case ZC_MUL: { uint32_t x = rf[in.a], y = rf[in.b]; rf[in.out] = hf::mul(x, y); break; }
-            case ZC_NEG: rf[in.out] = hf::neg(rf[in.a]); break;
-            case ZC_ASSERT: acc = acc + E4::load(alpha_pows + 4 * in.b) * rf[in.a]; break;
+    E4 acc = run(L);
+    // the same polynomial as a sum of self-contained pieces (the partition machine_create uses for the short rounds)
+    {
+        const size_t na = hp.assert_regs.size();
+        const size_t np_ = std::max<size_t>(1, std::min<size_t>(16, na / 4));
+        E4 sum;
+        for (size_t q = 0; q < np_; q++) {
+            ZcLowered P = zc_lower(hp, window, na * q / np_, na * (q + 1) / np_);
+            if (!P.error.empty() || P.n_regs > L.n_regs + 8) return -1;
+            sum = sum + run(P);
         }
+        sum.store(out + 8);
     }
     acc.store(out + 4);
     return (int)L.n_regs;

@@ -2,6 +2,7 @@
 // sp1-gpu/crates/sys/include/zerocheck/sequential.cuh:13-49) and LogUp interactions.
 #pragma once
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 struct DagInstr { uint8_t opcode, pad; uint16_t out, a, b; };
@@ -19,6 +20,8 @@ struct ChipProg {  // device pointers into the machine arena
 };
 struct HostProg {  // host copy for the padded-row adjustment (one evaluation on the all-zero row per proof)
     std::vector<DagInstr> instrs; std::vector<LeafRef> leaves; std::vector<uint32_t> consts, publics, assert_regs, assert_alphas;
+    // the same row polynomial as a sum of self-contained pieces (zc_lower.hpp): {offset into the chip's stream arena, length}
+    std::vector<std::pair<uint32_t, uint32_t>> zc_pieces;
 };
 
 struct sp1b200_machine {

@@ -25,7 +25,11 @@ static_assert(sizeof(ZcInstr) == 8, "ZcInstr is one 8-byte word");
 
 struct ZcLowered { std::vector<ZcInstr> instrs; uint32_t n_regs = 0; std::string error; };
 
-inline ZcLowered zc_lower(const HostProg& p, uint32_t window = 24) {
+// Lowers the sub-program needed for the asserts [assert_begin, assert_end) only (default: all of them).  A chip's row polynomial is
+// the SUM of its asserts, so the streams of a partition of the asserts can be interpreted by different threads and their row sums
+// added: the short late rounds of the sumcheck use such pieces (each self-contained: shared subexpressions are duplicated, the
+// reference's chunker does the same, sp1-gpu/crates/air/src/ir/chunker.rs) instead of one long stream per row pair.
+inline ZcLowered zc_lower(const HostProg& p, uint32_t window = 24, size_t assert_begin = 0, size_t assert_end = (size_t)-1) {
     ZcLowered L;
     const size_t n = p.instrs.size();
     const int32_t NONE = -1;
@@ -50,7 +54,8 @@ inline ZcLowered zc_lower(const HostProg& p, uint32_t window = 24) {
     }
     // asserts: value at the end of the program
     std::vector<std::vector<uint32_t>> asserts_of(n);
-    for (size_t k = 0; k < p.assert_regs.size(); k++) {
+    if (assert_end > p.assert_regs.size()) assert_end = p.assert_regs.size();
+    for (size_t k = assert_begin; k < assert_end; k++) {
         const int32_t v = cur[p.assert_regs[k] & 0xffff];
         if (v == NONE) { L.error = "assert on an undefined register"; return L; }
         if (p.assert_alphas[k] > 0xffff) { L.error = "more than 65536 constraints in one chip"; return L; }

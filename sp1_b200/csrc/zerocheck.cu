@@ -27,7 +27,8 @@ using kb::Ext;
 using hf::E4;
 
 constexpr int ZC_BLOCK = 128;
-constexpr int ZC_LOCAL_REGS = 128;  // fallback tier: register file in local memory
+constexpr int ZC_LOCAL_REGS = 128;
+constexpr size_t ZC_MAX_PIECES = 16;  // fallback tier: register file in local memory
 
 template <class K> struct Ops;
 template <> struct Ops<uint32_t> {
@@ -52,7 +53,8 @@ template <> struct Ops<Ext> {
 // one chip in one round
 struct ZcJob {
     const void* main; const void* prep; const uint32_t* alpha_pows; uint64_t h;
-    uint32_t blk_start, nblk, chip, pad;
+    uint32_t blk_start, nblk, chip, columns;   // columns != 0: this job also evaluates the opening-batching term
+    uint32_t zc_begin, zc_end, pad0, pad1;     // the piece of the chip's instruction stream this job interprets
 };
 struct ZcFixJob {
     const void* main; const void* prep; uint32_t* out; uint64_t h;
@@ -121,8 +123,8 @@ __global__ void __launch_bounds__(ZC_BLOCK) zc_sum_kernel(const ZcJob* __restric
     Ext acc[5];  // constraints at nodes 0,1,2 ; opening-batching term at 0 and at 1
 #pragma unroll
     for (int a = 0; a < 5; a++) acc[a] = kb::ext_zero();
-    const ZcInstr* __restrict__ zc = prog.zc;
-    const uint32_t n_zc = prog.n_zc;
+    const ZcInstr* __restrict__ zc = prog.zc + job.zc_begin;
+    const uint32_t n_zc = job.zc_end - job.zc_begin;
     for (uint64_t i = (uint64_t)(blockIdx.x - job.blk_start) * ZC_BLOCK + threadIdx.x; i < terms; i += (uint64_t)job.nblk * ZC_BLOCK) {
         const Ext e = kb::ext_load(E + 4 * i);
         Ext row[3] = {kb::ext_zero(), kb::ext_zero(), kb::ext_zero()};
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(ZC_BLOCK) zc_sum_kernel(const ZcJob* __restric
         }
 #pragma unroll
         for (int n = N0; n < 3; n++) acc[n] = kb::ext_add(acc[n], kb::ext_mul(row[n], e));
+        if (!job.columns) continue;
         // the opening-batching term is linear in the row variable: evaluate it at 0 and 1 only
         Ext s0 = kb::ext_zero(), s1 = kb::ext_zero();
         const bool has_o = 2 * i + 1 < h;
@@ -358,6 +361,18 @@ sp1b200_err sp1b200_machine_create(sp1b200_ctx* ctx, const uint32_t* h_blob, uin
         m->chips[c].n_zc = (uint32_t)L.instrs.size();
         m->chips[c].zc_regs = L.n_regs;
         all.insert(all.end(), L.instrs.begin(), L.instrs.end());
+        // pieces for the short rounds: the asserts split into up to ZC_MAX_PIECES contiguous groups of >= 4, each lowered on its own
+        const size_t na = m->host[c].assert_regs.size();
+        const size_t np_ = std::min<size_t>(ZC_MAX_PIECES, na / 4);
+        if (np_ >= 2 && L.instrs.size() >= 128) {
+            for (size_t q = 0; q < np_; q++) {
+                ZcLowered P = zc_lower(m->host[c], 24, na * q / np_, na * (q + 1) / np_);
+                if (!P.error.empty()) return sp1b200_set_error("machine_create: chip %u: %s", c, P.error.c_str());
+                m->host[c].zc_pieces.emplace_back((uint32_t)(all.size() - zc_off[c]), (uint32_t)P.instrs.size());
+                m->chips[c].zc_regs = std::max(m->chips[c].zc_regs, P.n_regs);
+                all.insert(all.end(), P.instrs.begin(), P.instrs.end());
+            }
+        }
     }
     SP1_CUDA(cudaMalloc(&m->d_zc_arena, all.size() * sizeof(ZcInstr) + 16));
     if (!all.empty()) SP1_CUDA(cudaMemcpyAsync(m->d_zc_arena, all.data(), all.size() * sizeof(ZcInstr), cudaMemcpyHostToDevice, ctx->stream));
@@ -496,10 +511,24 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
                     if (!hcur[k] || tier_of(p.zc_regs) != tier) continue;
                     unsigned nb = blocks_for((hcur[k] + 1) / 2, ZC_BLOCK);
                     if (nb > MAXB) nb = MAXB;
-                    ZcJob j{in_main(k), in_prep(k), d_ap + 4 * ap_off[k], hcur[k], Lc.blocks, nb, (uint32_t)k, 0};
-                    jobs.push_back(j);
-                    R.chip_of_job.push_back((uint32_t)k);
-                    Lc.n_jobs++; Lc.blocks += nb; Lc.regs = std::max(Lc.regs, p.zc_regs);
+                    // short rounds: a thread would interpret the whole program for its row pair (hundreds of microseconds for the
+                    // wide chips); the self-contained pieces run side by side instead, one job each
+                    const auto& pieces = m->host[k].zc_pieces;
+                    if (nb <= 16 && !pieces.empty()) {
+                        for (size_t q = 0; q < pieces.size(); q++) {
+                            ZcJob j{in_main(k), in_prep(k), d_ap + 4 * ap_off[k], hcur[k], Lc.blocks, nb, (uint32_t)k, q == 0 ? 1u : 0u,
+                                    pieces[q].first, pieces[q].first + pieces[q].second, 0, 0};
+                            jobs.push_back(j);
+                            R.chip_of_job.push_back((uint32_t)k);
+                            Lc.n_jobs++; Lc.blocks += nb;
+                        }
+                    } else {
+                        ZcJob j{in_main(k), in_prep(k), d_ap + 4 * ap_off[k], hcur[k], Lc.blocks, nb, (uint32_t)k, 1u, 0u, p.n_zc, 0, 0};
+                        jobs.push_back(j);
+                        R.chip_of_job.push_back((uint32_t)k);
+                        Lc.n_jobs++; Lc.blocks += nb;
+                    }
+                    Lc.regs = std::max(Lc.regs, p.zc_regs);
                 }
                 if (Lc.n_jobs) { R.sums.push_back(Lc); blocks_round += Lc.blocks; }
             }
@@ -549,7 +578,7 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     std::vector<E4> point;
     std::vector<E4> ys((size_t)nchips * 4);  // per chip: round polynomial values at the nodes 0, 1, 2, 4
     std::vector<uint32_t> hs((size_t)max_jobs * 36);
-    std::vector<int32_t> job_of_chip(nchips);
+    std::vector<E4> chip_sums(nchips * 9);
     const E4 two = E4::from_base(hf::to_monty(2)), four = E4::from_base(hf::to_monty(4)), three = E4::from_base(hf::to_monty(3));
     for (uint32_t rd = 0; rd < mlr; rd++) {
         const RoundPlan& R = plan[rd];
@@ -569,8 +598,10 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
             }
         }
         HostSpan sp_math(acc_math);
-        std::fill(job_of_chip.begin(), job_of_chip.end(), -1);
-        for (size_t j = 0; j < R.chip_of_job.size(); j++) job_of_chip[R.chip_of_job[j]] = (int32_t)j;
+        // a chip's sums = the sums of its jobs (one per piece of its instruction stream)
+        std::fill(chip_sums.begin(), chip_sums.end(), E4());
+        for (size_t j = 0; j < R.chip_of_job.size(); j++)
+            for (int w9 = 0; w9 < 9; w9++) chip_sums[(size_t)R.chip_of_job[j] * 9 + w9] = chip_sums[(size_t)R.chip_of_job[j] * 9 + w9] + E4::load(&hs[j * 36 + 4 * w9]);
         // Every chip's round polynomial goes through the same five nodes {0, 1, 2, 4, b} (b depends only on the shared point),
         // and interpolation is linear: combine the chips' node values with the lambda powers first, interpolate ONCE.
         const E4 last = gp[mlr - 1 - rd];
@@ -586,11 +617,11 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
             if (s.h == 0) { y[0] = y[1] = y[2] = y[3] = E4(); }
             else {
                 // sums: [node][slot] ; y_t = C_t + A + t (B - A) with A, B the opening-batching term at 0 and 1
-                const uint32_t* q = &hs[(size_t)job_of_chip[k] * 36];
-                const E4 A = E4::load(q + 4), B = E4::load(q + 8);
-                E4 y0 = E4::load(q) + A;
-                E4 y2 = E4::load(q + 12) + (B + B) - A;
-                E4 y4 = E4::load(q + 24) + B * four - A * three;
+                const E4* q = &chip_sums[k * 9];
+                const E4 A = q[1], B = q[2];
+                E4 y0 = q[0] + A;
+                E4 y2 = q[3] + (B + B) - A;
+                E4 y4 = q[6] + B * four - A * three;
                 const uint64_t th = (s.h + 1) / 2 - 1;
                 const uint64_t esize = (uint64_t)1 << (s.zeta.size() - 1);
                 // E[th] = eq(bits of th, zeta[0 .. len-1)) (most significant bit first): 21 host products instead of a device read + sync

@@ -64,7 +64,7 @@ def test_device_field_and_ext_sources_on_host():
 def _check_lowering(chip_words, main_w, prep_w, n_constraints, seed, window=24):
     rng = np.random.default_rng(seed)
     cw = np.array(chip_words, dtype=np.uint32)
-    out = np.zeros(8, np.uint32)
+    out = np.zeros(12, np.uint32)
     nl = C.c_uint32(0)
     regs = None
     for _ in range(6):
@@ -76,7 +76,8 @@ def _check_lowering(chip_words, main_w, prep_w, n_constraints, seed, window=24):
                                                pv.ctypes.data_as(O.u32p), ap.ctypes.data_as(O.u32p), C.c_uint32(window),
                                                out.ctypes.data_as(O.u32p), C.byref(nl))
         assert regs > 0
-        assert (out[:4] == out[4:]).all()
+        assert (out[:4] == out[4:8]).all()
+        assert (out[:4] == out[8:12]).all()     # ... and as a sum of self-contained pieces
         assert out[:4].any()          # random rows do not satisfy the constraints: a non-trivial comparison
     return regs, nl.value
 

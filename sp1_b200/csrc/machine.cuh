@@ -24,7 +24,13 @@ struct HostProg {  // host copy for the padded-row adjustment (one evaluation on
     std::vector<std::pair<uint32_t, uint32_t>> zc_pieces;
 };
 
+void sp1b200_free_interactions(void* p);
+
 struct sp1b200_machine {
+    sp1b200_machine() = default;
+    sp1b200_machine(const sp1b200_machine&) = delete;
+    sp1b200_machine& operator=(const sp1b200_machine&) = delete;
+    ~sp1b200_machine();  // zerocheck.cu: releases the device arenas and the interaction tables (also on a failed create)
     std::vector<ChipProg> chips;
     std::vector<HostProg> host;
     uint32_t* d_arena = nullptr;
@@ -34,4 +40,3 @@ struct sp1b200_machine {
 };
 
 void* sp1b200_parse_interactions(const uint32_t* b, const uint32_t* end, size_t n_chips);
-void sp1b200_free_interactions(void* p);

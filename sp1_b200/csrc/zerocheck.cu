@@ -320,6 +320,13 @@ inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n
 
 }  // namespace
 
+sp1b200_machine::~sp1b200_machine() {
+    if (interactions) sp1b200_free_interactions(interactions);
+    cudaFree(d_arena);
+    cudaFree(d_zc_arena);
+    cudaFree(d_chips);
+}
+
 extern "C" {
 
 // Upload a machine's constraint bytecode once (replaces upload_machine_bytecode, sp1-gpu/crates/zerocheck/src/prover.rs).
@@ -383,14 +390,7 @@ sp1b200_err sp1b200_machine_create(sp1b200_ctx* ctx, const uint32_t* h_blob, uin
     *out = m.release();
     return nullptr;
 }
-void sp1b200_machine_free(sp1b200_ctx*, sp1b200_machine* m) {
-    if (!m) return;
-    sp1b200_free_interactions(m->interactions);
-    cudaFree(m->d_arena);
-    cudaFree(m->d_zc_arena);
-    cudaFree(m->d_chips);
-    delete m;
-}
+void sp1b200_machine_free(sp1b200_ctx*, sp1b200_machine* m) { delete m; }
 // peak register pressure of a chip's re-scheduled program (tests / diagnostics)
 uint32_t sp1b200_machine_chip_regs(const sp1b200_machine* m, uint32_t chip) { return chip < m->chips.size() ? m->chips[chip].zc_regs : 0; }
 uint32_t sp1b200_machine_num_chips(const sp1b200_machine* m) { return (uint32_t)m->chips.size(); }

@@ -5,6 +5,7 @@
 #include "hostfield.hpp"
 #include "zc_lower.hpp"
 #include <cstring>
+#include <type_traits>
 
 extern "C" {
 void sp1b200_hostcheck_permute(uint32_t* states, uint64_t n) {
@@ -105,5 +106,31 @@ int sp1b200_hostcheck_zc_lower(const uint32_t* chip, const uint32_t* main_row, c
     }
     acc.store(out + 4);
     return (int)L.n_regs;
+}
+
+// Host transcript arithmetic (hostfield.hpp): product, inverse, and the batched-inversion Lagrange interpolation through 4 / 5 nodes
+// that the sumcheck drivers use.  coeffs_out: n ext elements = coefficients of the polynomial through (x_i, y_i).
+void sp1b200_hostcheck_e4(const uint32_t* a, const uint32_t* b, uint32_t* mul_out, uint32_t* inv_out, uint64_t n) {
+    using hf::E4;
+    for (uint64_t i = 0; i < n; i++) {
+        (E4::load(a + 4 * i) * E4::load(b + 4 * i)).store(mul_out + 4 * i);
+        hf::inv(E4::load(a + 4 * i)).store(inv_out + 4 * i);
+    }
+}
+int sp1b200_hostcheck_interpolate(const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t* coeffs_out) {
+    using hf::E4;
+    auto go = [&](auto tag) {
+        constexpr int N = decltype(tag)::value;
+        E4 x[N], L[N][N], c[N];
+        for (int i = 0; i < N; i++) x[i] = E4::load(xs + 4 * i);
+        hf::lagrange_basis<N>(x, L);
+        for (int k = 0; k < N; k++) for (int i = 0; i < N; i++) c[k] = c[k] + L[i][k] * E4::load(ys + 4 * i);
+        for (int k = 0; k < N; k++) c[k].store(coeffs_out + 4 * k);
+    };
+    if (n == 3) go(std::integral_constant<int, 3>{});
+    else if (n == 4) go(std::integral_constant<int, 4>{});
+    else if (n == 5) go(std::integral_constant<int, 5>{});
+    else return -1;
+    return 0;
 }
 }

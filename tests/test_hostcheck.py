@@ -124,3 +124,40 @@ def test_constraint_lowering_handles_register_reuse_dead_code_and_leaf_asserts()
     regs, n_low = _check_lowering(words, 2, 0, words[2], seed=99, window=2)
     assert regs <= 4
     assert dead >= 0
+
+
+def _ext_eval(coeffs, x):
+    """Horner with the oracle's ext arithmetic"""
+    L = O.lib()
+    acc = np.zeros(4, np.uint32)
+    tmp = np.zeros(4, np.uint32)
+    for c in coeffs[::-1]:
+        L.orc_ext_mul(O.ptr(acc), O.ptr(np.ascontiguousarray(x)), O.ptr(tmp))
+        acc = ((tmp.astype(np.uint64) + c) % O.P).astype(np.uint32)
+    return acc
+
+
+def test_host_transcript_arithmetic_matches_oracle():
+    """hostfield.hpp (the library's host transcript math): ext product / inverse vs the oracle, and the batched-inversion Lagrange
+    interpolation through 3, 4 and 5 nodes reproduces the node values"""
+    rng = np.random.default_rng(8)
+    n = 200
+    a, b = O.rand_field(rng, (n, 4)), O.rand_field(rng, (n, 4))
+    a[0] = O.P - 1; b[0] = O.P - 1; a[1] = [1, 0, 0, 0]
+    mul, inv = np.zeros((n, 4), np.uint32), np.zeros((n, 4), np.uint32)
+    _L().sp1b200_hostcheck_e4(a.ctypes.data_as(O.u32p), b.ctypes.data_as(O.u32p), mul.ctypes.data_as(O.u32p), inv.ctypes.data_as(O.u32p),
+                              C.c_uint64(n))
+    e = np.zeros(4, np.uint32)
+    for i in range(n):
+        O.lib().orc_ext_mul(O.ptr(a[i]), O.ptr(b[i]), O.ptr(e)); assert (mul[i] == e).all()
+        O.lib().orc_ext_inv(O.ptr(a[i]), O.ptr(e)); assert (inv[i] == e).all()
+    for deg in (3, 4, 5):
+        for _ in range(5):
+            xs, ys = O.rand_field(rng, (deg, 4)), O.rand_field(rng, (deg, 4))
+            xs[0] = 0                                    # the drivers' node sets start with 0 and 1
+            xs[1] = [int(O.to_monty(np.array([1]))[0]), 0, 0, 0]
+            coeffs = np.zeros((deg, 4), np.uint32)
+            assert _L().sp1b200_hostcheck_interpolate(xs.ctypes.data_as(O.u32p), ys.ctypes.data_as(O.u32p), C.c_uint32(deg),
+                                                      coeffs.ctypes.data_as(O.u32p)) == 0
+            for i in range(deg):
+                assert (_ext_eval(coeffs, xs[i]) == ys[i]).all()

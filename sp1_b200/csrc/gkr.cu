@@ -55,13 +55,18 @@ __device__ __forceinline__ Ext ldE(const uint32_t* p, uint64_t i) { return kb::e
 __device__ __forceinline__ void stE(uint32_t* p, uint64_t i, const Ext& e) { kb::ext_store(p + 4 * i, e); }
 
 // ---- level 0: per (chip, interaction k, row r) fraction from the trace (execution.rs:13-36, 114-252) -----------------------
+// q = a / b for work indices that almost always fit 32 bits: the 64-bit division (~60 instructions) only when needed
+__device__ __forceinline__ uint32_t div_small(uint64_t a, uint64_t b) {
+    return ((a | b) >> 32) ? (uint32_t)(a / b) : (uint32_t)a / (uint32_t)b;
+}
+
 __global__ void __launch_bounds__(256) gkr_first_level_kernel(const uint32_t* __restrict__ main, const uint32_t* __restrict__ prep, uint64_t h,
                                                               const InterDev* __restrict__ inter, uint32_t I, const VColDev* __restrict__ vcols,
                                                               const TermDev* __restrict__ terms, Ext alpha, const uint32_t* __restrict__ betas,
                                                               uint32_t* __restrict__ num, uint32_t* __restrict__ den) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= h * I) return;
-    const uint32_t k = (uint32_t)(t / h);
+    const uint32_t k = div_small(t, h);
     const uint64_t r = t - (uint64_t)k * h;
     const InterDev in = inter[k];
     auto apply = [&](const VColDev& v) {
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(256) gkr_level_kernel(JobTable jobs, const uin
     const ChipJob& c = jobs.j[find_job(jobs, w)];
     const uint64_t lw = w - c.work_start;
     const uint32_t len_o = (c.rows_in + 1) / 2;
-    const uint32_t k = (uint32_t)(lw / len_o);
+    const uint32_t k = div_small(lw, len_o);
     const uint32_t j = (uint32_t)(lw - (uint64_t)k * len_o);
     const uint64_t base = c.in_off + (uint64_t)k * c.rows_in;
     Ext n0 = ldE(num, base + 2 * j), d0 = ldE(den, base + 2 * j);
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(256) gkr_sum_seq_kernel(JobTable jobs, const u
         const ChipJob& c = jobs.j[find_job(jobs, w)];
         const uint64_t lw = w - c.work_start;
         const uint32_t rows = (c.rows_in + 1) / 2, pairs = (rows + 1) / 2;
-        const uint32_t k = (uint32_t)(lw / pairs), i = (uint32_t)(lw - (uint64_t)k * pairs);
+        const uint32_t k = div_small(lw, pairs), i = (uint32_t)(lw - (uint64_t)k * pairs);
         const uint64_t base = c.in_off + (uint64_t)k * c.rows_in;
         Row4 x = row_from_seq(num, den, base, c.rows_in, 2 * i), y = row_from_seq(num, den, base, c.rows_in, 2 * i + 1);
         pair_sums(x, y, ldE(eq_int, c.int_off + k), ldE(eq_row, 2 * i), ldE(eq_row, 2 * i + 1), lambda, s0, sh, se);
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(256) gkr_fix_sum_kernel(JobTable jobs, const u
         const uint64_t lw = w - c.work_start;
         const uint32_t rows_old = FROM_SEQ ? (c.rows_in + 1) / 2 : c.rows_in;
         const uint32_t rows_new = (rows_old + 1) / 2, pairs = (rows_new + 1) / 2;
-        const uint32_t k = (uint32_t)(lw / pairs), i = (uint32_t)(lw - (uint64_t)k * pairs);
+        const uint32_t k = div_small(lw, pairs), i = (uint32_t)(lw - (uint64_t)k * pairs);
         Row4 nr[2];
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {

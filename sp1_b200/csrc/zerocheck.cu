@@ -252,9 +252,14 @@ __global__ void __launch_bounds__(256) zc_fix_kernel(const ZcFixJob* __restrict_
     using O = Ops<K>;
     const ZcFixJob job = jobs[find_job(jobs, n_jobs, blockIdx.x)];
     const uint64_t h = job.h, nh = (h + 1) / 2;
-    const uint64_t t = (uint64_t)(blockIdx.x - job.blk_start) * 256 + threadIdx.x;
-    if (t >= nh * (job.main_w + job.prep_w)) return;
-    const uint64_t j = t / nh, i = t - j * nh;
+    // a block covers 256 consecutive row pairs of ONE column: (column, chunk) from the block index with one 32-bit division
+    // (a flat element index would cost a 64-bit division per element, comparable to the two field operations of the fold itself)
+    const uint32_t bpc = (uint32_t)((nh + 255) / 256);
+    const uint32_t lb = blockIdx.x - job.blk_start;
+    const uint64_t j = lb / bpc;
+    const uint64_t i = (uint64_t)(lb - (uint32_t)j * bpc) * 256 + threadIdx.x;
+    if (i >= nh) return;
+    const uint64_t t = j * nh + i;
     const K* in = j < job.main_w ? static_cast<const K*>(job.main) + j * h : static_cast<const K*>(job.prep) + (j - job.main_w) * h;
     K a = O::load(in, 2 * i);
     K b = (2 * i + 1 < h) ? O::load(in, 2 * i + 1) : O::zero();
@@ -542,7 +547,7 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
                 uint32_t* out = rd + 1 == mlr ? d_final + 4 * woff[k] : (rd & 1 ? d_buf[1] + boff1[k] : d_buf[0] + boff0[k]);
                 ZcFixJob f{in_main(k), in_prep(k), out, hcur[k], p.main_w, p.prep_w, R.fix_blocks, 0};
                 fjobs.push_back(f);
-                R.fix_jobs++; R.fix_blocks += blocks_for(nh * (p.main_w + p.prep_w), 256);
+                R.fix_jobs++; R.fix_blocks += blocks_for(nh, 256) * (p.main_w + p.prep_w);   // one column per block row (zc_fix_kernel)
                 hcur[k] = nh;
             }
         }

@@ -1,6 +1,7 @@
 // Context, memory and the kernel-level C entry points of include/sp1b200.h.
 #include "ctx.cuh"
 #include <atomic>
+#include <sched.h>
 #include <chrono>
 #include <cstring>
 #include <cstdarg>
@@ -154,6 +155,9 @@ sp1b200_err sp1b200_mail_wait(sp1b200_ctx* c, uint32_t seq) {
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif
+        // several contexts per GPU and several GPUs per host mean tens of polling threads: give the core away now and then so
+        // that an oversubscribed host (cgroup CPU quota) still schedules the threads that have work (free when nobody waits)
+        if ((spins & 0x3ff) == 0x3ff) sched_yield();
     }
 }
 

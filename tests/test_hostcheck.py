@@ -161,3 +161,66 @@ def test_host_transcript_arithmetic_matches_oracle():
                                                       coeffs.ctypes.data_as(O.u32p)) == 0
             for i in range(deg):
                 assert (_ext_eval(coeffs, xs[i]) == ys[i]).all()
+
+
+def _random_program(rng, n_instr, n_regs, main_w, prep_w, n_asserts):
+    """random NON-SSA bytecode: registers are overwritten at will, operands come from any register written so far, asserts
+    name arbitrary (written) registers — the shape a register-allocating compiler produces"""
+    from sp1_b200 import synth_air as SA
+    a = SA.Asm()
+    written = []
+    def emit(opc, out, x, y=0):
+        a.instrs.append((opc, out, x, y))
+        if out not in written:
+            written.append(out)
+    # seed a few registers with loads
+    for r in range(min(4, n_regs)):
+        kind = rng.integers(0, 3)
+        if kind == 0 or (kind == 1 and not prep_w):
+            a.leaves.append((SA.LEAF_MAIN, int(rng.integers(0, main_w)))); emit(SA.LOAD_LEAF, r, len(a.leaves) - 1)
+        elif kind == 1:
+            a.leaves.append((SA.LEAF_PREP, int(rng.integers(0, prep_w)))); emit(SA.LOAD_LEAF, r, len(a.leaves) - 1)
+        else:
+            a.consts.append(int(O.to_monty(np.array([int(rng.integers(0, 1000))]))[0])); emit(SA.LOAD_CONST, r, len(a.consts) - 1)
+    for _ in range(n_instr):
+        out = int(rng.integers(0, n_regs))
+        k = rng.integers(0, 10)
+        if k == 0:
+            a.leaves.append((SA.LEAF_MAIN, int(rng.integers(0, main_w)))); emit(SA.LOAD_LEAF, out, len(a.leaves) - 1)
+        elif k == 1 and prep_w:
+            a.leaves.append((SA.LEAF_PREP, int(rng.integers(0, prep_w)))); emit(SA.LOAD_LEAF, out, len(a.leaves) - 1)
+        elif k == 2:
+            a.publics.append(int(rng.integers(0, 8))); emit(SA.LOAD_PUBLIC, out, len(a.publics) - 1)
+        elif k == 3:
+            emit(SA.NEG, out, int(rng.choice(written)))
+        else:
+            emit([SA.ADD, SA.SUB, SA.MUL][int(rng.integers(0, 3))], out, int(rng.choice(written)), int(rng.choice(written)))
+    a.nreg = n_regs
+    for _ in range(n_asserts):
+        a.assert_zero(int(rng.choice(written)))
+    return a.words(main_w, prep_w)
+
+
+def test_constraint_lowering_fuzz():
+    """random register-reusing programs: the re-scheduled stream and its partition into pieces evaluate to the same row
+    polynomial as the bytecode as given; the lowered pressure never exceeds the number of registers the input used by much"""
+    rng = np.random.default_rng(2024)
+    for it in range(60):
+        n_regs = int(rng.integers(2, 40))
+        main_w, prep_w = int(rng.integers(1, 30)), int(rng.integers(0, 4))
+        n_instr = int(rng.integers(1, 400))
+        n_asserts = int(rng.integers(1, 60))
+        words = _random_program(rng, n_instr, n_regs, main_w, prep_w, n_asserts)
+        cw = np.array(words, dtype=np.uint32)
+        out = np.zeros(12, np.uint32)
+        nl = C.c_uint32(0)
+        for window in (0, 24):
+            mr, pr, pv = O.rand_field(rng, main_w), O.rand_field(rng, max(prep_w, 1)), O.rand_field(rng, 8)
+            ap = O.rand_field(rng, (n_asserts, 4))
+            regs = _L().sp1b200_hostcheck_zc_lower(cw.ctypes.data_as(O.u32p), mr.ctypes.data_as(O.u32p), pr.ctypes.data_as(O.u32p),
+                                                   pv.ctypes.data_as(O.u32p), ap.ctypes.data_as(O.u32p), C.c_uint32(window),
+                                                   out.ctypes.data_as(O.u32p), C.byref(nl))
+            assert regs > 0, (it, window)
+            assert (out[:4] == out[4:8]).all(), (it, window, "full stream")
+            assert (out[:4] == out[8:12]).all(), (it, window, "pieces")
+            assert regs <= n_regs + 4, (it, window, regs, n_regs)

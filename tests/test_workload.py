@@ -1,0 +1,51 @@
+"""Synthetic workload generator (sp1_b200/workload.py, sp1_b200/synth_air.py): shapes follow the reference's bench generator
+(sp1-gpu/crates/jagged_tracegen/src/test_utils.rs:107-221) — heights multiples of 32 up to 2^22, target areas within 1 %, chips
+in name order — and the synthetic traces satisfy their own constraints and balanced interactions (checked by the oracle)."""
+import numpy as np
+import pytest
+
+from sp1_b200 import synth_air as SA
+from sp1_b200 import workload as W
+from tests import oracle_lib as O
+
+
+@pytest.mark.parametrize("name", ["S1", "S2", "S3", "tiny"])
+def test_shard_shapes(name):
+    prep, main = W.shard_shapes(name)
+    area = W.area_of(main)
+    target = W.WORKLOADS[name][0]
+    assert abs(area - target) <= 0.01 * target
+    assert all(r % 32 == 0 and 0 <= r <= 1 << 22 for r, _ in main)
+    assert sum(1 for r, _ in main if r == 0) >= 1            # absent chips stay in the list with height 0
+    assert [c for _, c in main] == [w for _, w in sorted(W.CORE_CHIPS)]
+    assert (W.shard_shapes(name) == (prep, main))            # deterministic for a seed
+    assert W.shard_shapes(name, seed=43)[1] != main
+
+
+def test_synthetic_machine_is_consistent():
+    m = W.synthetic_machine("tiny", seed=42)
+    assert m["names"] == sorted(m["names"])
+    assert len(m["names"]) == len(m["specs"]) == len(m["main_shapes"])
+    for (h, g, wp), (rows, cols) in zip(m["specs"], m["main_shapes"]):
+        assert rows == h and cols == 6 * g + (1 if wp else 0)
+    assert int(m["blob"][0]) == len(m["specs"])
+    small = W.synthetic_machine("S2", seed=42, scale=1 / 64)
+    assert W.area_of(small["main_shapes"]) < W.area_of(W.synthetic_machine("S2", seed=42)["main_shapes"]) / 32
+
+
+def test_synthetic_traces_satisfy_constraints_and_interactions():
+    """a scaled-down copy of the bench machine: the oracle proves it and its restated verifier accepts (constraints hold on every
+    real row, the LogUp cumulative sum is zero)"""
+    m = W.synthetic_machine("tiny", seed=42, scale=1 / 256)
+    rng = np.random.default_rng(3)
+    mains, preps = [], []
+    for h, g, wp in m["specs"]:
+        a, p = SA.synth_trace(rng, h, g, wp, 12345)
+        mains.append(a); preps.append(p)
+    pv = O.to_monty(np.array([12345, 5, 6, 7]))
+    heights = [h for h, _, _ in m["specs"]]
+    mlr = max(5, int(np.ceil(np.log2(max(heights + [2])))))
+    ch = O.Challenger()
+    pc, words = O.prove_shard_verify(m["blob"], heights, mains, preps, m["names"], pv, min(mlr, 6), mlr, ch, num_queries=4, pow_bits=2,
+                                     batch_pow_bits=1, gkr_pow_bits=2)
+    assert words[0] == 5 and words.size > 100

@@ -184,6 +184,9 @@ typedef struct sp1b200_machine sp1b200_machine; /* the machine's AIR constraints
 sp1b200_err sp1b200_machine_create(sp1b200_ctx* ctx, const uint32_t* h_blob, uint64_t n_words, sp1b200_machine** out);
 void sp1b200_machine_free(sp1b200_ctx* ctx, sp1b200_machine* machine);
 uint32_t sp1b200_machine_num_chips(const sp1b200_machine* machine);
+/* diagnostic: peak number of live registers of a chip's re-scheduled constraint program (selects the register-file tier of the
+ * zerocheck kernels: <= 32 shared memory, <= 128 local memory, more is rejected by sp1b200_zerocheck); 0 if chip is out of range */
+uint32_t sp1b200_machine_chip_regs(const sp1b200_machine* machine, uint32_t chip);
 
 /* ShardProver::zerocheck (crates/hypercube/src/prover/shard.rs:474-646): samples lambda, runs the max_log_row_count-round
  * sumcheck over all chips (round polynomial through nodes {0,1,2,4,b}, crates/hypercube/src/prover/zerocheck/sum_as_poly.rs:187-287),

@@ -45,6 +45,7 @@ def load():
         L.sp1b200_challenger_sample_bits.restype = C.c_uint32
         L.sp1b200_challenger_check_witness.restype = C.c_int
         L.sp1b200_machine_num_chips.restype = C.c_uint32
+        L.sp1b200_machine_chip_regs.restype = C.c_uint32
         for name in ERR_FUNCS:
             getattr(L, name).restype = C.c_char_p
         _cdll = L
@@ -61,7 +62,7 @@ ERR_FUNCS = [
 OTHER_FUNCS = ["sp1b200_challenger_init", "sp1b200_challenger_observe", "sp1b200_challenger_sample",
                "sp1b200_challenger_sample_bits", "sp1b200_challenger_check_witness", "sp1b200_ctx_destroy", "sp1b200_default_core_params", "sp1b200_version", "sp1b200_ctx_stream",
                "sp1b200_launch_count", "sp1b200_last_phase_ms", "sp1b200_commit_free", "sp1b200_jagged_round_free",
-               "sp1b200_machine_free", "sp1b200_machine_num_chips"]
+               "sp1b200_machine_free", "sp1b200_machine_num_chips", "sp1b200_machine_chip_regs"]
 
 
 def _ptr(a):

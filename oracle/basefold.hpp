@@ -19,7 +19,9 @@ static inline std::vector<EF> partial_lagrange(const std::vector<EF>& point) {
     std::vector<EF> ev{EF::one()};
     for (const EF& x : point) {
         std::vector<EF> nx(ev.size() * 2);
-        for (size_t i = 0; i < ev.size(); i++) {
+        const size_t m = ev.size();
+#pragma omp parallel for schedule(static) if (m >= 4096)
+        for (size_t i = 0; i < m; i++) {
             EF prod = ev[i] * x;
             nx[2 * i] = ev[i] - prod;
             nx[2 * i + 1] = prod;
@@ -33,8 +35,15 @@ template <class T>
 static inline EF mle_eval(const T* vals, size_t len, const std::vector<EF>& point, size_t stride = 1) {
     std::vector<EF> eq = partial_lagrange(point);
     size_t n = len < eq.size() ? len : eq.size();
-    EF acc;
-    for (size_t i = 0; i < n; i++) acc += eq[i] * vals[i * stride];
+    EF acc;  // exact field arithmetic: any summation order gives the same words
+#pragma omp parallel if (n >= 4096)
+    {
+        EF l;
+#pragma omp for schedule(static) nowait
+        for (size_t i = 0; i < n; i++) l += eq[i] * vals[i * stride];
+#pragma omp critical
+        acc += l;
+    }
     return acc;
 }
 
@@ -95,6 +104,7 @@ static inline BasefoldProof basefold_prove(std::vector<EF> eval_point, const std
     if (replay_witnesses) { pf.batch_grinding_witness = replay_witnesses[0]; bool ok = ch.check_witness(fp.batch_pow_bits, replay_witnesses[0]); assert(ok); (void)ok; }
     else pf.batch_grinding_witness = ch.grind(fp.batch_pow_bits);
 
+    OrcTrace* t_b = new OrcTrace("basefold.batch+encode");
     size_t total_len = 0;
     for (auto& r : rounds) total_len += r->ncols;
     unsigned nb = log2_ceil(total_len);
@@ -121,11 +131,15 @@ static inline BasefoldProof basefold_prove(std::vector<EF> eval_point, const std
     std::vector<EF> cw(n);
     {
         std::vector<F> limbs(4 * h), enc(4 * n);
+#pragma omp parallel for schedule(static)
         for (size_t i = 0; i < h; i++) for (int l = 0; l < 4; l++) limbs[l * h + i] = mle[i].c[l];
         rs_encode_columns(limbs.data(), 4, log_h, fp.log_blowup, enc.data());
+#pragma omp parallel for schedule(static)
         for (size_t i = 0; i < n; i++) for (int l = 0; l < 4; l++) cw[i].c[l] = enc[l * n + i];
     }
 
+    delete t_b;
+    OrcTrace* t_f = new OrcTrace("basefold.fold_rounds");
     ch.observe(F::from_canonical(log_h));
     std::vector<std::vector<F>> round_leaves;
     std::vector<MerkleTree> round_trees;
@@ -143,6 +157,7 @@ static inline BasefoldProof basefold_prove(std::vector<EF> eval_point, const std
         size_t m = cw.size();
         unsigned log_m = log2_ceil(m);
         std::vector<F> leaves(m * 4);
+#pragma omp parallel for schedule(static) if (m >= 4096)
         for (size_t i = 0; i < m; i++) for (int l = 0; l < 4; l++) leaves[i * 4 + l] = cw[i].c[l];
         MerkleTree t = merkle_commit_rows(leaves.data(), 8, log_m - 1);
         ch.observe(t.commitment);
@@ -152,6 +167,7 @@ static inline BasefoldProof basefold_prove(std::vector<EF> eval_point, const std
         // fold codeword: f[i] = (1/2 + beta/(2 x_i)) e0 + (1/2 - beta/(2 x_i)) e1, x_i = g^{bitrev(i, log_m-1)}, g of order m
         std::vector<EF> fcw(m / 2);
         F ginv = two_adic_generator(log_m).inv();
+#pragma omp parallel for schedule(static) if (m >= 4096)
         for (size_t i = 0; i < m / 2; i++) {
             F xinv = ginv.pow(reverse_bits_len((uint32_t)i, log_m - 1));
             EF pw = beta * (half * xinv);
@@ -160,12 +176,15 @@ static inline BasefoldProof basefold_prove(std::vector<EF> eval_point, const std
         cw.swap(fcw);
         // fold mle
         std::vector<EF> fm(mle.size() / 2);
+#pragma omp parallel for schedule(static) if (fm.size() >= 4096)
         for (size_t i = 0; i < fm.size(); i++) fm[i] = mle[2 * i] + beta * mle[2 * i + 1];
         mle.swap(fm);
         claim = zero_val + beta * one_val;
         round_leaves.push_back(std::move(leaves));
         round_trees.push_back(std::move(t));
     }
+    delete t_f;
+    OrcTrace t_q("basefold.grind+queries");
     pf.final_poly = cw[0];
     ch.observe_ext(pf.final_poly);
     if (replay_witnesses) { pf.pow_witness = replay_witnesses[1]; bool ok = ch.check_witness(fp.pow_bits, replay_witnesses[1]); assert(ok); (void)ok; }

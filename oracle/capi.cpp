@@ -80,6 +80,8 @@ extern "C" {
 // bench.py cpu_baseline support: skip the (restated) verifier and report the phase times of the last jagged run
 void orc_set_skip_verify(int v) { g_skip_verify = v; }
 void orc_last_times(double* out4) { for (int i = 0; i < 4; i++) out4[i] = g_times[i]; }
+static double g_shard_times[5] = {0, 0, 0, 0, 0};  // seconds of the last orc_prove_shard_verify: prep commit, main commit, LogUp-GKR, zerocheck, jagged/BaseFold open
+void orc_shard_times(double* out5) { for (int i = 0; i < 5; i++) out5[i] = g_shard_times[i]; }
 
 int orc_num_threads() {
 #ifdef _OPENMP
@@ -112,6 +114,31 @@ void orc_ext_mul(const uint32_t* a, const uint32_t* b, uint32_t* out) {
 void orc_ext_inv(const uint32_t* a, uint32_t* out) {
     EF r = EF::from_base_slice(asF(a)).inv();
     for (int i = 0; i < 4; i++) out[i] = r.c[i].v;
+}
+
+// primitives exported so that tests can pin them to the reference's CUDA kernels (oracle/_ref): eq table, batching, folds
+void orc_partial_lagrange(const uint32_t* point, uint64_t n_vars, uint32_t* out) {
+    std::vector<EF> p(n_vars);
+    for (uint64_t i = 0; i < n_vars; i++) p[i] = EF::from_base_slice(asF(point + 4 * i));
+    std::vector<EF> eq = partial_lagrange(p);
+    for (size_t i = 0; i < eq.size(); i++) for (int k = 0; k < 4; k++) out[4 * i + k] = eq[i].c[k].v;
+}
+// out[row] = sum_c coeff[c] * mat[c][row]   (the BaseFold batching of columns, basefold-prover/src/prover.rs:140-170)
+void orc_batch_columns(const uint32_t* mat, uint64_t width, uint64_t height, const uint32_t* coeffs, uint32_t* out) {
+    for (uint64_t r = 0; r < height; r++) {
+        EF acc;
+        for (uint64_t c = 0; c < width; c++) acc += EF::from_base_slice(asF(coeffs + 4 * c)) * F::raw(mat[c * height + r]);
+        for (int k = 0; k < 4; k++) out[4 * r + k] = acc.c[k].v;
+    }
+}
+// out[i] = in[2i] + beta * in[2i+1]   (multilinear/src/fold.rs:12-26)  and  out[i] = in[2i] + alpha (in[2i+1] - in[2i])
+void orc_fold_ext(const uint32_t* in, uint64_t m, const uint32_t* beta, int fix_last, uint32_t* out) {
+    EF b = EF::from_base_slice(asF(beta));
+    for (uint64_t i = 0; i < m; i++) {
+        EF e = EF::from_base_slice(asF(in + 8 * i)), o = EF::from_base_slice(asF(in + 8 * i + 4));
+        EF r = fix_last ? e + b * (o - e) : e + b * o;
+        for (int k = 0; k < 4; k++) out[4 * i + k] = r.c[k].v;
+    }
 }
 
 // ---- poseidon2 ---------------------------------------------------------------------------------
@@ -432,12 +459,15 @@ int64_t orc_prove_shard_verify(const uint32_t* machine_blob, const uint64_t* hei
     const bool has_prep = !ptabs.empty();
     // setup: preprocessed commit (AirProver::setup, shard.rs:406-429)
     JaggedRound prep_round;
+    double t0 = now_s();
     if (has_prep) { prep_round = jagged_commit(ptabs, log_stack, max_log_rows, fp); for (int i = 0; i < 8; i++) prep_commit_out[i] = prep_round.commit.d[i].v; }
+    g_shard_times[0] = now_s() - t0; t0 = now_s();
     Challenger ch; chal_load(ch, challenger_state);
     Challenger vch = ch;
     // ---- prove
     ch.observe_slice(pv.data(), pv.size());
     JaggedRound main_round = jagged_commit(mtabs, log_stack, max_log_rows, fp);
+    g_shard_times[1] = now_s() - t0; t0 = now_s();
     ch.observe(main_round.commit);
     ch.observe(F::from_canonical(n));
     for (size_t k = 0; k < n; k++) {
@@ -445,6 +475,7 @@ int64_t orc_prove_shard_verify(const uint32_t* machine_blob, const uint64_t* hei
         for (unsigned char b : nm[k]) ch.observe(F::from_canonical(b));
     }
     GkrProof gp = gkr_prove(gchips, max_log_rows, gkr_pow_bits, ch);
+    g_shard_times[2] = now_s() - t0; t0 = now_s();
     EF alpha = ch.sample_ext(), gamma = ch.sample_ext();
     std::vector<EF> claims(n);
     for (size_t k = 0; k < n; k++) {
@@ -454,11 +485,13 @@ int64_t orc_prove_shard_verify(const uint32_t* machine_blob, const uint64_t* hei
         claims[k] = a;
     }
     ZerocheckResult zr = zerocheck_prove(zchips, alpha, gamma, gp.point, claims, pv, max_log_rows, ch);
+    g_shard_times[3] = now_s() - t0; t0 = now_s();
     std::vector<JaggedRound> rounds;
     std::vector<std::vector<EF>> jclaims;
     if (has_prep) { rounds.push_back(prep_round); std::vector<EF> c; for (auto& o : zr.opened) c.insert(c.end(), o.prep.begin(), o.prep.end()); jclaims.push_back(c); }
     { rounds.push_back(main_round); std::vector<EF> c; for (auto& o : zr.opened) c.insert(c.end(), o.main.begin(), o.main.end()); jclaims.push_back(c); }
     JaggedProof jp = jagged_prove(zr.proof.point, jclaims, rounds, max_log_rows, ch, fp);
+    g_shard_times[4] = now_s() - t0;
     chal_store(ch, challenger_state);
     // ---- verify (verify_shard order)
     if (!g_skip_verify) {

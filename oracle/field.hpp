@@ -10,6 +10,9 @@
 //   :255-268 (mul), :450-467 (inverse);  kb31_extension_t.cuh:6-63,108-160 (ext4, W = 3).
 // In-memory representation (u32 Montgomery word) is byte-compatible with p3's KoalaBear.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstddef>
 #include <cassert>
@@ -125,6 +128,13 @@ struct EF {
 };
 
 static inline EF operator*(F s, const EF& e) { return e * s; }
+
+// ORC_TRACE=1: scoped wall-clock spans on stderr (profiling the CPU arm of bench.py; no effect on results)
+struct OrcTrace {
+    const char* name; std::chrono::steady_clock::time_point t0; bool on;
+    explicit OrcTrace(const char* n) : name(n), t0(std::chrono::steady_clock::now()) { static const bool e = std::getenv("ORC_TRACE") != nullptr; on = e; }
+    ~OrcTrace() { if (on) std::fprintf(stderr, "[orc] %-28s %8.3f s\n", name, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()); }
+};
 
 static inline uint32_t reverse_bits_len(uint32_t x, unsigned bits) {
     uint32_t r = 0;

@@ -60,14 +60,18 @@ static inline Layer first_layer(const std::vector<GkrChip>& chips, const EF& alp
         ChipLayer cl; cl.I = c.inter.size(); cl.rows = (c.height + 1) / 2; total += cl.I;
         cl.n0.assign(cl.rows * cl.I, EF()); cl.n1 = cl.n0;
         cl.d0.assign(cl.rows * cl.I, EF::one()); cl.d1 = cl.d0;
-        std::vector<F> mr(c.main_w), pr(c.prep_w);
-        for (size_t r = 0; r < c.height; r++) {
-            for (size_t j = 0; j < c.main_w; j++) mr[j] = c.main[j * c.height + r];
-            for (size_t j = 0; j < c.prep_w; j++) pr[j] = c.prep[j * c.height + r];
-            for (size_t k = 0; k < cl.I; k++) {
-                auto [m, d] = interaction_vals<F>(c.inter[k], pr.data(), mr.data(), alpha, betas);
-                size_t idx = (r / 2) * cl.I + k;
-                if (r & 1) { cl.n1[idx] = EF(m); cl.d1[idx] = d; } else { cl.n0[idx] = EF(m); cl.d0[idx] = d; }
+#pragma omp parallel if (c.height * cl.I >= 4096)
+        {
+            std::vector<F> mr(c.main_w), pr(c.prep_w);
+#pragma omp for schedule(static)
+            for (size_t r = 0; r < c.height; r++) {   // every (row, interaction) writes its own slot
+                for (size_t j = 0; j < c.main_w; j++) mr[j] = c.main[j * c.height + r];
+                for (size_t j = 0; j < c.prep_w; j++) pr[j] = c.prep[j * c.height + r];
+                for (size_t k = 0; k < cl.I; k++) {
+                    auto [m, d] = interaction_vals<F>(c.inter[k], pr.data(), mr.data(), alpha, betas);
+                    size_t idx = (r / 2) * cl.I + k;
+                    if (r & 1) { cl.n1[idx] = EF(m); cl.d1[idx] = d; } else { cl.n0[idx] = EF(m); cl.d0[idx] = d; }
+                }
             }
         }
         L.chips.push_back(std::move(cl));
@@ -82,6 +86,7 @@ static inline Layer transition(const Layer& L) {
         ChipLayer cl; cl.I = c.I; cl.rows = (c.rows + 1) / 2;
         cl.n0.assign(cl.rows * cl.I, EF()); cl.n1 = cl.n0;
         cl.d0.assign(cl.rows * cl.I, EF::one()); cl.d1 = cl.d0;
+#pragma omp parallel for schedule(static) if (cl.rows * cl.I >= 4096)
         for (size_t i = 0; i < cl.rows; i++)
             for (size_t k = 0; k < c.I; k++) {
                 size_t e = (2 * i) * c.I + k, o = (2 * i + 1) * c.I + k, t = i * c.I + k;
@@ -132,7 +137,12 @@ static inline GkrRoundProof prove_round(Layer L, const std::vector<EF>& eval_poi
         if (!interaction_mode) {
             size_t off = 0;
             for (auto& c : L.chips) {
-                for (size_t i = 0; i < (c.rows + 1) / 2; i++) {
+                const size_t half_rows = (c.rows + 1) / 2;
+#pragma omp parallel if (half_rows * c.I >= 2048)
+                {
+                EF le0, leh, leqs;   // exact field arithmetic: any summation order gives the same words
+#pragma omp for schedule(static) nowait
+                for (size_t i = 0; i < half_rows; i++) {
                     EF er0 = eq_row[2 * i], er1 = eq_row[2 * i + 1];
                     bool full = 2 * i + 1 < c.rows;
                     EF a0, ah, es;
@@ -145,7 +155,10 @@ static inline GkrRoundProof prove_round(Layer L, const std::vector<EF>& eval_poi
                         ah += e * (lambda * ((d0 + d0b) * (n1 + n1b) + (d1 + d1b) * (n0 + n0b)) + (d0 + d0b) * (d1 + d1b));
                         es += e * (er0 + er1);
                     }
-                    e0 += a0 * er0; eh += ah * (er0 + er1); eqs += es;
+                    le0 += a0 * er0; leh += ah * (er0 + er1); leqs += es;
+                }
+#pragma omp critical
+                { e0 += le0; eh += leh; eqs += leqs; }
                 }
                 off += c.I;
             }
@@ -180,6 +193,7 @@ static inline GkrRoundProof prove_round(Layer L, const std::vector<EF>& eval_poi
             for (auto& c : L.chips) {
                 size_t nr = (c.rows + 1) / 2;
                 std::vector<EF> n0(nr * c.I), n1(nr * c.I), d0(nr * c.I), d1(nr * c.I);
+#pragma omp parallel for schedule(static) if (nr * c.I >= 2048)
                 for (size_t i = 0; i < nr; i++)
                     for (size_t k = 0; k < c.I; k++) {
                         size_t x = (2 * i) * c.I + k, y = (2 * i + 1) * c.I + k, t = i * c.I + k;
@@ -190,6 +204,7 @@ static inline GkrRoundProof prove_round(Layer L, const std::vector<EF>& eval_poi
                 c.n0.swap(n0); c.n1.swap(n1); c.d0.swap(d0); c.d1.swap(d1); c.rows = nr;
             }
             std::vector<EF> ne(eq_row.size() / 2);
+#pragma omp parallel for schedule(static) if (ne.size() >= 4096)
             for (size_t i = 0; i < ne.size(); i++) ne[i] = fix(eq_row[2 * i], eq_row[2 * i + 1]);
             eq_row.swap(ne);
             if (L.num_row_vars == 1) {
@@ -240,8 +255,8 @@ static inline GkrProof gkr_prove(const std::vector<GkrChip>& chips, unsigned mlr
     (void)ch.sample_ext();  // _pv_challenge
     std::vector<EF> betas = partial_lagrange(beta_seed);
     std::vector<Layer> layers;
-    layers.push_back(first_layer(chips, alpha, betas, mlr));
-    while (layers.back().num_row_vars > 1) layers.push_back(transition(layers.back()));
+    { OrcTrace t("gkr.first_layer"); layers.push_back(first_layer(chips, alpha, betas, mlr)); }
+    { OrcTrace t("gkr.transitions"); while (layers.back().num_row_vars > 1) layers.push_back(transition(layers.back())); }
     outputs(layers.back(), pf.out_num, pf.out_den);
     ch.observe_variable_length_ext_slice(pf.out_num.data(), pf.out_num.size());
     ch.observe_variable_length_ext_slice(pf.out_den.data(), pf.out_den.size());
@@ -249,6 +264,7 @@ static inline GkrProof gkr_prove(const std::vector<GkrChip>& chips, unsigned mlr
     std::vector<EF> eval_point = ch.sample_point(v + 1);
     EF num_eval = mle_eval(pf.out_num.data(), pf.out_num.size(), eval_point);
     EF den_eval = mle_eval(pf.out_den.data(), pf.out_den.size(), eval_point);
+    OrcTrace* t_r = new OrcTrace("gkr.rounds");
     while (!layers.empty()) {
         GkrRoundProof rp = prove_round(std::move(layers.back()), eval_point, num_eval, den_eval, ch);
         layers.pop_back();
@@ -260,13 +276,20 @@ static inline GkrProof gkr_prove(const std::vector<GkrChip>& chips, unsigned mlr
         eval_point.push_back(lc);
         pf.rounds.push_back(std::move(rp));
     }
+    delete t_r;
+    OrcTrace t_o("gkr.openings");
     pf.point = last_k(eval_point, mlr);
     std::vector<EF> eq = partial_lagrange(pf.point);
     ch.observe(F::from_canonical(chips.size()));
     for (auto& c : chips) {
         std::vector<EF> mo(c.main_w), po(c.prep_w);
-        for (size_t j = 0; j < c.main_w; j++) for (size_t r = 0; r < c.height; r++) mo[j] += eq[r] * c.main[j * c.height + r];
-        for (size_t j = 0; j < c.prep_w; j++) for (size_t r = 0; r < c.height; r++) po[j] += eq[r] * c.prep[j * c.height + r];
+#pragma omp parallel for schedule(dynamic, 1)
+        for (size_t j = 0; j < c.main_w + c.prep_w; j++) {
+            const F* col = j < c.main_w ? c.main + j * c.height : c.prep + (j - c.main_w) * c.height;
+            EF a;
+            for (size_t r = 0; r < c.height; r++) a += eq[r] * col[r];
+            (j < c.main_w ? mo[j] : po[j - c.main_w]) = a;
+        }
         if (c.prep_w) ch.observe_variable_length_ext_slice(po.data(), po.size());
         ch.observe_variable_length_ext_slice(mo.data(), mo.size());
         pf.main_open.push_back(mo); pf.prep_open.push_back(po);

@@ -97,6 +97,7 @@ static inline std::vector<EF> jagged_little_poly(const JaggedParams& jp, const s
     std::vector<EF> col_eq = partial_lagrange(last_k(z_col, log2_ceil(ncols)));
     std::vector<EF> row_eq = partial_lagrange(last_k(z_row, jp.max_log_rows));
     std::vector<EF> out(total);
+#pragma omp parallel for schedule(dynamic, 1)
     for (size_t c = 0; c < ncols; c++)
         for (size_t i = jp.prefix[c]; i < jp.prefix[c + 1]; i++) out[i] = col_eq[c] * row_eq[i - jp.prefix[c]];
     return out;
@@ -297,6 +298,7 @@ struct JaggedProof {
 static inline JaggedProof jagged_prove(const std::vector<EF>& z_row, const std::vector<std::vector<EF>>& claims,
                                        const std::vector<JaggedRound>& rounds, unsigned max_log_rows, Challenger& ch,
                                        const FriParams& fp, const F* replay_witnesses = nullptr) {
+    OrcTrace* t_pre = new OrcTrace("jagged.setup");
     size_t total_cols = 0;
     for (auto& r : rounds) for (size_t c : r.col_counts) total_cols += c;
     std::vector<EF> z_col = ch.sample_point(log2_ceil(total_cols));
@@ -311,19 +313,73 @@ static inline JaggedProof jagged_prove(const std::vector<EF>& z_row, const std::
     JaggedParams jp = jagged_params(heights, max_log_rows);
     unsigned lm = jp.log_m();
     size_t N = (size_t)1 << lm;
-    std::vector<EF> ext = jagged_little_poly(jp, z_row, z_col);
-    std::vector<EF> base(N);  // after the first fix the base becomes EF; start by lifting
-    {
-        size_t off = 0;
-        for (auto& r : rounds) { for (F v : r.stacked->mles) base[off++] = EF(v); }
-    }
+    delete t_pre;
+    // Round 0 reads the committed base-field words and the jagged little polynomial (partial_jagged_little_polynomial_evaluation,
+    // poly.rs:251-296: value at long-vector index i = col_eq[c] * row_eq[i - prefix[c]]) in place: neither the 2^log_m EF lift of the
+    // trace nor the 2^log_m little polynomial is materialised (same field values, a quarter of the memory).
+    const size_t ncols_j = jp.prefix.size() - 1;
+    const std::vector<EF> col_eq = partial_lagrange(last_k(z_col, log2_ceil(ncols_j)));
+    const std::vector<EF> row_eq = partial_lagrange(last_k(z_row, jp.max_log_rows));
+    std::vector<std::pair<size_t, const F*>> segs;   // (first index, words) of each round's stacked buffer in the long vector
+    { size_t off = 0; for (auto& r : rounds) { segs.push_back({off, r.stacked->mles.data()}); off += r.stacked->mles.size(); } segs.push_back({off, nullptr}); }
+    auto base_at = [&](size_t idx) -> F {
+        size_t k = 0;
+        while (k + 2 < segs.size() && segs[k + 1].first <= idx) k++;
+        return idx < segs.back().first ? segs[k].second[idx - segs[k].first] : F();
+    };
+    auto col_of = [&](size_t idx) { return (size_t)(std::upper_bound(jp.prefix.begin(), jp.prefix.end(), idx) - jp.prefix.begin()) - 1; };
+    auto ext_at = [&](size_t idx, size_t& c) -> EF {   // c: cursor, never ahead of idx's column
+        if (idx >= jp.prefix.back()) return EF();
+        while (jp.prefix[c + 1] <= idx) c++;
+        return col_eq[c] * row_eq[idx - jp.prefix[c]];
+    };
     EF claim = mle_eval(column_claims.data(), column_claims.size(), z_col);
     JaggedProof pf;
     pf.sumcheck.claimed_sum = claim;
     EF half = EF(F::two().inv()), quarter = EF(F::from_canonical(4).inv());
     std::vector<EF> point;
     EF round_claim = claim;
-    for (unsigned rd = 0; rd < lm; rd++) {
+    OrcTrace* t_sc = new OrcTrace("jagged.hadamard_sumcheck");
+    std::vector<EF> base, ext;
+    {
+        EF e0, eh;
+#pragma omp parallel
+        {
+            EF l0, lh;
+            size_t c = 0; bool init = false;
+#pragma omp for schedule(static) nowait
+            for (size_t i = 0; i < N / 2; i++) {
+                if (!init) { c = std::min(col_of(2 * i), ncols_j - 1); init = true; }
+                const EF x0 = ext_at(2 * i, c), x1 = ext_at(2 * i + 1, c);
+                const F b0 = base_at(2 * i), b1 = base_at(2 * i + 1);
+                l0 += x0 * b0;
+                lh += (x0 + x1) * (b0 + b1);
+            }
+#pragma omp critical
+            { e0 += l0; eh += lh; }
+        }
+        EF e1 = round_claim - e0;
+        Uni poly = interpolate({EF(), EF::one(), half}, {e0, e1, eh * quarter});
+        ch.observe_ext_slice(poly.c.data(), poly.c.size());
+        pf.sumcheck.polys.push_back(poly);
+        EF alpha = ch.sample_ext();
+        point.insert(point.begin(), alpha);
+        base.resize(N / 2); ext.resize(N / 2);
+#pragma omp parallel
+        {
+            size_t c = 0; bool init = false;
+#pragma omp for schedule(static)
+            for (size_t i = 0; i < N / 2; i++) {
+                if (!init) { c = std::min(col_of(2 * i), ncols_j - 1); init = true; }
+                const EF x0 = ext_at(2 * i, c), x1 = ext_at(2 * i + 1, c);
+                const F b0 = base_at(2 * i), b1 = base_at(2 * i + 1);
+                base[i] = EF(b0) + alpha * (b1 - b0);
+                ext[i] = x0 + alpha * (x1 - x0);
+            }
+        }
+        round_claim = poly.eval(alpha);
+    }
+    for (unsigned rd = 1; rd < lm; rd++) {
         size_t n = base.size();
         EF e0, eh;
 #pragma omp parallel
@@ -354,8 +410,9 @@ static inline JaggedProof jagged_prove(const std::vector<EF>& z_row, const std::
     }
     pf.sumcheck.point = point;
     pf.sumcheck.eval = round_claim;
+    delete t_sc;
     EF base_eval = base[0];
-    pf.jagged_eval = jagged_eval_prove(jp, z_row, z_col, point, ch);
+    { OrcTrace t("jagged.eval_sumcheck"); pf.jagged_eval = jagged_eval_prove(jp, z_row, z_col, point, ch); }
     std::vector<std::shared_ptr<StackedRound>> srounds;
     for (auto& r : rounds) {
         srounds.push_back(r.stacked);
@@ -366,7 +423,7 @@ static inline JaggedProof jagged_prove(const std::vector<EF>& z_row, const std::
     }
     // prove_untrusted_evaluation: observe the claim, then the stacked proof
     ch.observe_ext(base_eval);
-    pf.pcs = stacked_prove(point, srounds, ch, fp, replay_witnesses);
+    { OrcTrace t("jagged.stacked_prove"); pf.pcs = stacked_prove(point, srounds, ch, fp, replay_witnesses); }
     pf.expected_eval = base_eval;
     pf.max_log_rows = max_log_rows;
     pf.log_m = lm;

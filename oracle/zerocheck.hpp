@@ -107,13 +107,14 @@ struct State {
     const AirProgram* air;
 };
 
+// E = partial_lagrange(zeta without its last coordinate): every chip with rows carries the same zeta in a given round, so the
+// caller builds the table once per round
 template <class K>
-static Uni sum_as_poly(const State& s, const std::vector<K>& M, const std::vector<K>& Pp, const F* pv, bool first, const EF& claim) {
+static Uni sum_as_poly(const State& s, const std::vector<K>& M, const std::vector<K>& Pp, const F* pv, bool first, const EF& claim,
+                       const std::vector<EF>& E) {
     Uni out;
     if (s.h == 0) { out.c.assign(5, EF()); return out; }
-    std::vector<EF> rest(s.zeta.begin(), s.zeta.end() - 1);
     EF last = s.zeta.back();
-    std::vector<EF> E = partial_lagrange(rest);
     size_t terms = (s.h + 1) / 2;
     EF y0, y2, y4;
 #pragma omp parallel
@@ -168,6 +169,7 @@ template <class K>
 static void fix_cols(const std::vector<K>& in, size_t h, size_t w, const EF& alpha, std::vector<EF>& out) {
     size_t nh = (h + 1) / 2;
     out.assign(nh * w, EF());
+#pragma omp parallel for schedule(static) if (nh * w >= 4096)
     for (size_t i = 0; i < nh; i++)
         for (size_t c = 0; c < w; c++) {
             EF a = EF(in[(2 * i) * w + c]);
@@ -195,6 +197,7 @@ static inline ZerocheckResult zerocheck_prove(const std::vector<ZcChip>& chips, 
         EF g = gkr_challenge;
         for (size_t j = 0; j < c.main_w + c.prep_w; j++) { s.gkr_pows.push_back(g); g *= gkr_challenge; }
         s.mF.resize(c.height * c.main_w); s.pF.resize(c.height * c.prep_w);
+#pragma omp parallel for schedule(static) if (c.height >= 1024)
         for (size_t r = 0; r < c.height; r++) {
             for (size_t j = 0; j < c.main_w; j++) s.mF[r * c.main_w + j] = c.main[j * c.height + r];
             for (size_t j = 0; j < c.prep_w; j++) s.pF[r * c.prep_w + j] = c.prep[j * c.height + r];
@@ -211,9 +214,10 @@ static inline ZerocheckResult zerocheck_prove(const std::vector<ZcChip>& chips, 
     std::vector<EF> round_claims = claims;
     std::vector<Uni> unis(chips.size());
     for (unsigned rd = 0; rd < max_log_rows; rd++) {
+        std::vector<EF> E = partial_lagrange(std::vector<EF>(gkr_point.begin(), gkr_point.end() - rd - 1));
         for (size_t k = 0; k < chips.size(); k++)
-            unis[k] = rd == 0 ? sum_as_poly<F>(st[k], st[k].mF, st[k].pF, pv.data(), true, round_claims[k])
-                              : sum_as_poly<EF>(st[k], st[k].mE, st[k].pE, pv.data(), false, round_claims[k]);
+            unis[k] = rd == 0 ? sum_as_poly<F>(st[k], st[k].mF, st[k].pF, pv.data(), true, round_claims[k], E)
+                              : sum_as_poly<EF>(st[k], st[k].mE, st[k].pE, pv.data(), false, round_claims[k], E);
         Uni rlc; rlc.c.assign(1, EF());
         for (auto& u : unis) {
             size_t n = std::max(rlc.c.size(), u.c.size());

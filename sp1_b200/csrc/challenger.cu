@@ -175,7 +175,7 @@ sp1b200_err HostChallenger::grind(uint32_t bits, uint32_t* w_monty) {
     return nullptr;
 }
 
-extern "C" sp1b200_err sp1b200_grind(sp1b200_ctx* ctx, uint32_t* h_state34, uint32_t bits, uint32_t* h_witness) {
+extern "C" sp1b200_err sp1b200_grind(sp1b200_ctx* ctx, uint32_t* h_state34, uint32_t bits, uint32_t* h_witness) { SP1_DEVICE_GUARD(ctx);
     HostChallenger ch;
     SP1_TRY(ch.init(ctx, h_state34));
     PhaseTimer t(ctx, "grind");

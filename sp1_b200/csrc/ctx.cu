@@ -67,16 +67,10 @@ void sp1b200_default_core_params(sp1b200_params* p) {
     p->pow_bits = 16; p->batch_pow_bits = 5; p->gkr_pow_bits = 12; p->grind_mode = 0;
 }
 
-sp1b200_err sp1b200_ctx_create(int device, const sp1b200_params* params, sp1b200_ctx** out) {
-    if (!out) return sp1b200_set_error("ctx_create: out is NULL");
-    int ndev = 0;
-    SP1_CUDA(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) return sp1b200_set_error("ctx_create: device %d not present (%d devices)", device, ndev);
-    SP1_CUDA(cudaSetDevice(device));
+static sp1b200_err ctx_init(sp1b200_ctx* c, int device, const sp1b200_params* params) {
     cudaDeviceProp prop;
     SP1_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return sp1b200_set_error("ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-    sp1b200_ctx* c = new sp1b200_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     if (params) c->params = *params; else sp1b200_default_core_params(&c->params);
@@ -105,25 +99,48 @@ sp1b200_err sp1b200_ctx_create(int device, const sp1b200_params* params, sp1b200
     SP1_CUDA(cudaHostGetDevicePointer((void**)&c->d_mail, c->h_mail, 0));
     SP1_CUDA(cudaMalloc((void**)&c->d_mail_counter, 64));
     SP1_CUDA(cudaMemset(c->d_mail_counter, 0, 64));
-    sp1b200_err e = sp1b200_init_tables(c);
-    if (e) { delete c; return e; }
+    SP1_TRY(sp1b200_init_tables(c));
     SP1_CUDA(cudaStreamSynchronize(c->stream));
+    return nullptr;
+}
+
+sp1b200_err sp1b200_ctx_create(int device, const sp1b200_params* params, sp1b200_ctx** out) {
+    if (!out) return sp1b200_set_error("ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    SP1_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return sp1b200_set_error("ctx_create: device %d not present (%d devices)", device, ndev);
+    Sp1DeviceGuard guard(device);
+    sp1b200_ctx* c = new sp1b200_ctx();
+    c->device = device;
+    sp1b200_err e = ctx_init(c, device, params);
+    if (e) {  // every failure exit releases what was created so far (destroy null-checks each member)
+        sp1b200_ctx_destroy(c);
+        return e;
+    }
     *out = c;
     return nullptr;
 }
 
 void sp1b200_ctx_destroy(sp1b200_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_TH); cudaFree(c->d_TL);
-    cudaFree(c->d_mail_counter);
+    SP1_DEVICE_GUARD(c);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->d_TH) cudaFree(c->d_TH);
+    if (c->d_TL) cudaFree(c->d_TL);
+    if (c->d_mail_counter) cudaFree(c->d_mail_counter);
     if (c->h_mail) cudaFreeHost(c->h_mail);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
-    for (int i = 0; i < 2; i++) { cudaFree(c->d_slot[i]); if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]); if (c->slot_free[i]) cudaEventDestroy(c->slot_free[i]); }
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    for (int i = 0; i < 2; i++) {
+        if (c->d_slot[i]) cudaFree(c->d_slot[i]);
+        if (c->slot_ready[i]) cudaEventDestroy(c->slot_ready[i]);
+        if (c->slot_free[i]) cudaEventDestroy(c->slot_free[i]);
+    }
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
     if (c->pool) cudaMemPoolDestroy(c->pool);
+    cudaGetLastError();
     delete c;
 }
 
@@ -165,7 +182,7 @@ sp1b200_err sp1b200_mail_wait(sp1b200_ctx* c, uint32_t seq) {
 // device pointer.  The copy overlaps whatever the main stream is doing (normally the proof of the previous shard); a later
 // call on the main stream that consumes the pointer (sp1b200_prove_shard / sp1b200_jagged_commit) waits for it in stream
 // order, and the slot is not overwritten before its previous consumer has finished.
-sp1b200_err sp1b200_upload_begin(sp1b200_ctx* c, const uint32_t* h_src, uint64_t n_words, int slot, uint32_t** d_out) {
+sp1b200_err sp1b200_upload_begin(sp1b200_ctx* c, const uint32_t* h_src, uint64_t n_words, int slot, uint32_t** d_out) { SP1_DEVICE_GUARD(c);
     if (slot < 0 || slot > 1) return sp1b200_set_error("upload_begin: slot must be 0 or 1");
     if (!h_src || !d_out) return sp1b200_set_error("upload_begin: NULL argument");
     if (c->slot_words[slot] < n_words) {
@@ -183,7 +200,7 @@ sp1b200_err sp1b200_upload_begin(sp1b200_ctx* c, const uint32_t* h_src, uint64_t
     return nullptr;
 }
 // stream-ordered wait for a pending upload if `d_ptr` is one of the slots; returns the slot index or -1
-int sp1b200_upload_acquire(sp1b200_ctx* c, const void* d_ptr) {
+int sp1b200_upload_acquire(sp1b200_ctx* c, const void* d_ptr) { SP1_DEVICE_GUARD(c);
     for (int i = 0; i < 2; i++)
         if (d_ptr && d_ptr == c->d_slot[i]) {
             if (c->slot_pending[i]) { cudaStreamWaitEvent(c->stream, c->slot_ready[i], 0); c->slot_pending[i] = false; }
@@ -191,11 +208,11 @@ int sp1b200_upload_acquire(sp1b200_ctx* c, const void* d_ptr) {
         }
     return -1;
 }
-void sp1b200_upload_release(sp1b200_ctx* c, int slot) {
+void sp1b200_upload_release(sp1b200_ctx* c, int slot) { SP1_DEVICE_GUARD(c);
     if (slot >= 0 && slot < 2) cudaEventRecord(c->slot_free[slot], c->stream);
 }
 
-sp1b200_err sp1b200_ctx_sync(sp1b200_ctx* c) {
+sp1b200_err sp1b200_ctx_sync(sp1b200_ctx* c) { SP1_DEVICE_GUARD(c);
     SP1_CUDA(cudaStreamSynchronize(c->stream));
     if (c->copy_stream) SP1_CUDA(cudaStreamSynchronize(c->copy_stream));
     return nullptr;
@@ -207,25 +224,25 @@ float sp1b200_last_phase_ms(sp1b200_ctx* c, const char* phase) {
     return it == c->phase_ms.end() ? -1.0f : it->second;
 }
 
-sp1b200_err sp1b200_malloc(sp1b200_ctx* c, size_t bytes, void** d_out) {
+sp1b200_err sp1b200_malloc(sp1b200_ctx* c, size_t bytes, void** d_out) { SP1_DEVICE_GUARD(c);
     SP1_CUDA(cudaMallocFromPoolAsync(d_out, bytes, c->pool, c->stream));
     return nullptr;
 }
-sp1b200_err sp1b200_free(sp1b200_ctx* c, void* d_ptr) {
+sp1b200_err sp1b200_free(sp1b200_ctx* c, void* d_ptr) { SP1_DEVICE_GUARD(c);
     if (d_ptr) SP1_CUDA(cudaFreeAsync(d_ptr, c->stream));
     return nullptr;
 }
-sp1b200_err sp1b200_memcpy_h2d(sp1b200_ctx* c, void* d_dst, const void* h_src, size_t bytes) {
+sp1b200_err sp1b200_memcpy_h2d(sp1b200_ctx* c, void* d_dst, const void* h_src, size_t bytes) { SP1_DEVICE_GUARD(c);
     SP1_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
     return nullptr;
 }
-sp1b200_err sp1b200_memcpy_d2h(sp1b200_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
+sp1b200_err sp1b200_memcpy_d2h(sp1b200_ctx* c, void* h_dst, const void* d_src, size_t bytes) { SP1_DEVICE_GUARD(c);
     SP1_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
     SP1_CUDA(cudaStreamSynchronize(c->stream));
     return nullptr;
 }
 
-sp1b200_err sp1b200_poseidon2_permute(sp1b200_ctx* c, uint32_t* states_any, uint64_t n) {
+sp1b200_err sp1b200_poseidon2_permute(sp1b200_ctx* c, uint32_t* states_any, uint64_t n) { SP1_DEVICE_GUARD(c);
     DevBuf b;
     SP1_TRY(b.in(c, states_any, n * 16 * sizeof(uint32_t)));
     if (b.owned) b.host = states_any;
@@ -236,7 +253,7 @@ sp1b200_err sp1b200_poseidon2_permute(sp1b200_ctx* c, uint32_t* states_any, uint
 }
 
 sp1b200_err sp1b200_rs_encode(sp1b200_ctx* c, const uint32_t* msg_any, uint64_t ncols, uint32_t log_h, uint32_t log_blowup,
-                              uint32_t* out_any) {
+                              uint32_t* out_any) { SP1_DEVICE_GUARD(c);
     DevBuf in, out;
     size_t n = (size_t)ncols << log_h;
     SP1_TRY(in.in(c, msg_any, n * sizeof(uint32_t)));
@@ -249,7 +266,7 @@ sp1b200_err sp1b200_rs_encode(sp1b200_ctx* c, const uint32_t* msg_any, uint64_t 
 }
 
 sp1b200_err sp1b200_merkle_commit(sp1b200_ctx* c, const uint32_t* mat_any, uint64_t width, uint32_t log_h, uint32_t* d_layers_out,
-                                  uint32_t* h_root8, uint32_t* h_commit8) {
+                                  uint32_t* h_root8, uint32_t* h_commit8) { SP1_DEVICE_GUARD(c);
     DevBuf in;
     SP1_TRY(in.in(c, mat_any, ((size_t)width << log_h) * sizeof(uint32_t)));
     uint32_t* layers = d_layers_out;

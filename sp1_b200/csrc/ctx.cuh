@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../include/sp1b200.h"
@@ -38,6 +39,7 @@ struct sp1b200_ctx {
     cudaEvent_t slot_ready[2] = {nullptr, nullptr};   // recorded on copy_stream after the upload
     cudaEvent_t slot_free[2] = {nullptr, nullptr};    // recorded on stream when the consumer (prove_shard) is done with the slot
     bool slot_pending[2] = {false, false};
+    std::unique_ptr<uint32_t[]> shard_scratch;  // host staging of the three variable-length proof sections (shard.cu), reused across shards
 };
 constexpr size_t SP1_MAIL_HDR = 16;               // words before the payload (64-byte aligned payload)
 constexpr size_t SP1_MAIL_WORDS = 1 << 16;        // payload capacity in words (256 KiB)
@@ -68,6 +70,22 @@ __device__ __forceinline__ void sp1_mail_done(const Mail& m) {
 #endif
 
 const char* sp1b200_set_error(const char* fmt, ...);
+
+// Every extern "C" entry point that takes a context runs with the context's device current and restores the caller's device on
+// exit: the CUDA current device is per host thread and defaults to 0, so a host runtime that drives several GPUs from one process
+// (worker threads, tokio spawn_blocking) would otherwise allocate and launch on the wrong device.
+struct Sp1DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit Sp1DeviceGuard(int dev) {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~Sp1DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    Sp1DeviceGuard(const Sp1DeviceGuard&) = delete;
+    Sp1DeviceGuard& operator=(const Sp1DeviceGuard&) = delete;
+};
+#define SP1_DEVICE_GUARD(c) Sp1DeviceGuard _sp1_device_guard((c) ? (c)->device : -1)
 
 #define SP1_CUDA(call)                                                                            \
     do {                                                                                          \

@@ -484,7 +484,7 @@ extern "C" {
 // dense_any: the tables' real cells back to back, each table column-major [cols x rows] (tables with 0 rows
 // contribute nothing), host or device; the library keeps its own zero-padded device copy.
 sp1b200_err sp1b200_jagged_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, uint32_t n_tables, const uint64_t* rows, const uint64_t* cols,
-                                  int keep_codeword, uint32_t* h_commit8, sp1b200_jagged_round** out) {
+                                  int keep_codeword, uint32_t* h_commit8, sp1b200_jagged_round** out) { SP1_DEVICE_GUARD(ctx);
     const uint32_t ls = ctx->params.log_stacking_height, mlr = ctx->params.max_log_row_count;
     auto r = std::make_unique<sp1b200_jagged_round>();
     uint64_t area = 0;
@@ -498,11 +498,12 @@ sp1b200_err sp1b200_jagged_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, u
     r->area = area; r->padded_area = padded;
     SP1_CUDA(cudaMallocFromPoolAsync((void**)&r->d_dense, padded * 4, ctx->pool, ctx->stream));
     const int up_slot = sp1b200_upload_acquire(ctx, dense_any);  // dense_any may be an upload slot still being filled
-    if (area) SP1_CUDA(cudaMemcpyAsync(r->d_dense, dense_any, area * 4, cudaMemcpyDefault, ctx->stream));
+    cudaError_t ce = area ? cudaMemcpyAsync(r->d_dense, dense_any, area * 4, cudaMemcpyDefault, ctx->stream) : cudaSuccess;
     sp1b200_upload_release(ctx, up_slot);                        // the slot is free once this copy has run
-    if (added) SP1_CUDA(cudaMemsetAsync(r->d_dense + area, 0, added * 4, ctx->stream));
-    sp1b200_err e = sp1b200_stacked_commit(ctx, r->d_dense, padded / S, keep_codeword, r->original_commit, &r->stacked);
-    if (e) { cudaFreeAsync(r->d_dense, ctx->stream); return e; }
+    if (ce == cudaSuccess && added) ce = cudaMemsetAsync(r->d_dense + area, 0, added * 4, ctx->stream);
+    sp1b200_err e = ce == cudaSuccess ? sp1b200_stacked_commit(ctx, r->d_dense, padded / S, keep_codeword, r->original_commit, &r->stacked)
+                                      : sp1b200_set_error("jagged_commit: copying the dense trace: %s", cudaGetErrorString(ce));
+    if (e) { cudaFreeAsync(r->d_dense, ctx->stream); r->d_dense = nullptr; return e; }
     const uint64_t added_cols = std::max<uint64_t>((added + R - 1) / R, 1);
     r->row_counts.push_back(R); r->row_counts.push_back(added - (added_cols - 1) * R);
     r->col_counts.push_back(added_cols - 1); r->col_counts.push_back(1);
@@ -518,7 +519,7 @@ sp1b200_err sp1b200_jagged_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, u
     return nullptr;
 }
 
-void sp1b200_jagged_round_free(sp1b200_ctx* ctx, sp1b200_jagged_round* r) {
+void sp1b200_jagged_round_free(sp1b200_ctx* ctx, sp1b200_jagged_round* r) { SP1_DEVICE_GUARD(ctx);
     if (!r) return;
     sp1b200_commit_free(ctx, r->stacked);
     if (r->d_dense) cudaFreeAsync(r->d_dense, ctx->stream);
@@ -527,7 +528,7 @@ void sp1b200_jagged_round_free(sp1b200_ctx* ctx, sp1b200_jagged_round* r) {
 
 // Per-column evaluations of every table column of the round at z_row (zero-padded to 2^max_log_row_count rows):
 // the claims zerocheck hands to the PCS (crates/hypercube/src/prover/shard.rs:736-767).  h_out: sum(cols) ext elements.
-sp1b200_err sp1b200_jagged_column_claims(sp1b200_ctx* ctx, const sp1b200_jagged_round* r, const uint32_t* h_z_row, uint32_t* h_out) {
+sp1b200_err sp1b200_jagged_column_claims(sp1b200_ctx* ctx, const sp1b200_jagged_round* r, const uint32_t* h_z_row, uint32_t* h_out) { SP1_DEVICE_GUARD(ctx);
     const uint32_t mlr = ctx->params.max_log_row_count;
     DevFree mem(ctx);
     uint32_t *d_z, *d_eq, *d_out;
@@ -560,7 +561,7 @@ sp1b200_err sp1b200_jagged_column_claims(sp1b200_ctx* ctx, const sp1b200_jagged_
 // max_log_row_count | log_m        (field order of JaggedPcsProof, slop/crates/jagged/src/verifier.rs:17-27)
 sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* rounds, uint32_t n_rounds, const uint32_t* h_z_row,
                                  const uint32_t* h_claims, const uint32_t* h_replay, uint32_t* h_chal, uint32_t* h_proof, uint64_t cap,
-                                 uint64_t* h_words) {
+                                 uint64_t* h_words) { SP1_DEVICE_GUARD(ctx);
     if (!n_rounds || n_rounds > 8) return sp1b200_set_error("jagged_prove: 1..8 rounds supported");
     const uint32_t mlr = ctx->params.max_log_row_count, ls = ctx->params.log_stacking_height;
     cudaStream_t st = ctx->stream;

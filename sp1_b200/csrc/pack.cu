@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) transpose_table_kernel(const uint32_t* __
 }  // namespace
 
 extern "C" sp1b200_err sp1b200_pack_row_major(sp1b200_ctx* ctx, const uint32_t* rows_any, uint32_t n_tables, const uint64_t* rows,
-                                              const uint64_t* cols, uint32_t* d_dense_out) {
+                                              const uint64_t* cols, uint32_t* d_dense_out) { SP1_DEVICE_GUARD(ctx);
     if (!rows || !cols) return sp1b200_set_error("pack_row_major: NULL shape arrays");
     uint64_t total = 0;
     for (uint32_t t = 0; t < n_tables; t++) {

@@ -238,7 +238,7 @@ inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n
 extern "C" {
 
 sp1b200_err sp1b200_stacked_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, uint64_t ncols, int keep_codeword,
-                                   uint32_t* h_commit8, sp1b200_commit** out) {
+                                   uint32_t* h_commit8, sp1b200_commit** out) { SP1_DEVICE_GUARD(ctx);
     if (!ncols) return sp1b200_set_error("stacked_commit: ncols == 0");
     const uint32_t log_h = ctx->params.log_stacking_height, b = ctx->params.log_blowup;
     const size_t n = (size_t)ncols << log_h, M = n << b;
@@ -277,7 +277,7 @@ sp1b200_err sp1b200_stacked_commit(sp1b200_ctx* ctx, const uint32_t* dense_any, 
     return nullptr;
 }
 
-void sp1b200_commit_free(sp1b200_ctx* ctx, sp1b200_commit* c) {
+void sp1b200_commit_free(sp1b200_ctx* ctx, sp1b200_commit* c) { SP1_DEVICE_GUARD(ctx);
     if (!c) return;
     if (c->owns_mles) cudaFreeAsync(c->d_mles, ctx->stream);
     if (c->d_codeword) cudaFreeAsync(c->d_codeword, ctx->stream);
@@ -287,7 +287,7 @@ void sp1b200_commit_free(sp1b200_ctx* ctx, sp1b200_commit* c) {
 
 sp1b200_err sp1b200_stacked_prove(sp1b200_ctx* ctx, sp1b200_commit* const* rounds, uint32_t n_rounds, const uint32_t* h_point,
                                   uint32_t n_point, const uint32_t* h_replay, uint32_t* h_chal, uint32_t* h_proof,
-                                  uint64_t cap, uint64_t* h_words) {
+                                  uint64_t cap, uint64_t* h_words) { SP1_DEVICE_GUARD(ctx);
     using hf::E4;
     if (!n_rounds) return sp1b200_set_error("stacked_prove: no rounds");
     const uint32_t log_h = rounds[0]->log_h, b = rounds[0]->log_blowup;

@@ -29,7 +29,7 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx*, const sp1b200_machine*, const uint64
 // h_replay_witnesses (grind_mode == 1): {gkr witness, batch grinding witness, pow witness}.
 sp1b200_err sp1b200_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* m, sp1b200_jagged_round* prep_round, const uint32_t* main_dense_any,
                                 const uint64_t* h_heights, const char* const* chip_names, const uint32_t* h_pv, uint32_t n_pv,
-                                const uint32_t* h_replay_witnesses, uint32_t* h_chal, uint32_t* h_proof, uint64_t cap, uint64_t* h_words) {
+                                const uint32_t* h_replay_witnesses, uint32_t* h_chal, uint32_t* h_proof, uint64_t cap, uint64_t* h_words) { SP1_DEVICE_GUARD(ctx);
     using hf::E4;
     const size_t nch = m->chips.size();
     const uint32_t mlr = ctx->params.max_log_row_count;
@@ -77,15 +77,18 @@ sp1b200_err sp1b200_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* m, sp1b
     }
     uint32_t st[34];
     ch.store(st);
-    // uninitialised scratch for the phase outputs (zero-filling 3 x 64 MiB would cost more than some of the phases)
+    // per-context scratch for the phase outputs, allocated once and reused by every shard proven on this context (uninitialised:
+    // zero-filling 3 x 64 MiB per shard would cost more than some of the phases)
     const uint64_t scratch_cap = (uint64_t)1 << 24;
-    std::unique_ptr<uint32_t[]> gkr_buf(new uint32_t[scratch_cap]), zc_buf(new uint32_t[scratch_cap]), ev_buf(new uint32_t[scratch_cap]);
-    uint32_t* gkr = gkr_buf.get();
+    if (!ctx->shard_scratch) ctx->shard_scratch.reset(new uint32_t[3 * scratch_cap]);
+    uint32_t* gkr = ctx->shard_scratch.get();
     uint64_t n_gkr = 0;
     SP1_TRY(sp1b200_logup_gkr(ctx, m, h_heights, d_main.data(), d_prep.data(), h_replay_witnesses, st, gkr, scratch_cap, &n_gkr));
     // tail of the gkr words: point (mlr ext) | per chip {main, prep openings} | witness
     size_t total_w = 0;
     for (auto& c : m->chips) total_w += c.main_w + c.prep_w;
+    if (n_gkr < 1 + 4 * total_w + 4 * (uint64_t)mlr)
+        return sp1b200_set_error("prove_shard: LogUp-GKR section has %llu words, fewer than its point + openings + witness tail", (unsigned long long)n_gkr);
     const uint32_t* tail = gkr + n_gkr - 1 - 4 * total_w - 4 * mlr;
     const uint32_t* gkr_point = tail;
     const uint32_t* openings = tail + 4 * mlr;
@@ -102,11 +105,14 @@ sp1b200_err sp1b200_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* m, sp1b
         }
     }
     ch.store(st);
-    uint32_t* zc = zc_buf.get();
+    uint32_t* zc = gkr + scratch_cap;
     uint64_t n_zc = 0;
     SP1_TRY(sp1b200_zerocheck(ctx, m, h_heights, d_main.data(), d_prep.data(), h_pv, n_pv, gkr_point, alpha.c, gamma.c, claims.data(), st, zc,
                               scratch_cap, &n_zc));
     // zerocheck words: [mlr] { [5] coeffs(20) } x mlr | claimed_sum 4 | point 4 mlr | eval 4 | per chip {prep evals, main evals}
+    if (n_zc != 1 + (uint64_t)mlr * 21 + 4 + 4 * (uint64_t)mlr + 4 + 4 * total_w || zc[0] != mlr)
+        return sp1b200_set_error("prove_shard: zerocheck section has %llu words, layout expects %llu", (unsigned long long)n_zc,
+                                 (unsigned long long)(1 + (uint64_t)mlr * 21 + 4 + 4 * (uint64_t)mlr + 4 + 4 * total_w));
     const uint32_t* zpoint = zc + 1 + (size_t)mlr * 21 + 4;
     const uint32_t* zopen = zpoint + 4 * mlr + 4;
     std::vector<uint32_t> jclaims;
@@ -123,15 +129,17 @@ sp1b200_err sp1b200_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* m, sp1b
     std::vector<sp1b200_jagged_round*> rounds;
     if (prep_round) rounds.push_back(prep_round);
     rounds.push_back(main_round);
-    uint32_t* ev = ev_buf.get();
+    uint32_t* ev = gkr + 2 * scratch_cap;
     uint64_t n_ev = 0;
     SP1_TRY(sp1b200_jagged_prove(ctx, rounds.data(), (uint32_t)rounds.size(), zpoint, jclaims.data(), h_replay_witnesses ? h_replay_witnesses + 1 : nullptr,
                                  st, ev, scratch_cap, &n_ev));
-    memcpy(h_chal, st, sizeof(st));
     const uint64_t total = 6 + 8 + n_gkr + n_zc + n_ev + n_pv;
     t_all.stop();
     if (h_words) *h_words = total;
-    if (total > cap) return sp1b200_set_error("prove_shard: proof needs %llu words, capacity %llu", (unsigned long long)total, (unsigned long long)cap);
+    // the caller's challenger is advanced only together with a delivered proof: on a capacity error h_chal is untouched and
+    // *h_words holds the size to retry with
+    if (h_proof && total > cap) return sp1b200_set_error("prove_shard: proof needs %llu words, capacity %llu", (unsigned long long)total, (unsigned long long)cap);
+    memcpy(h_chal, st, sizeof(st));
     if (h_proof) {
         uint32_t* o = h_proof;
         const uint32_t hdr[6] = {5, 8, (uint32_t)n_gkr, (uint32_t)n_zc, (uint32_t)n_ev, n_pv};

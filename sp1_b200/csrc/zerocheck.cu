@@ -337,29 +337,53 @@ extern "C" {
 // Upload a machine's constraint bytecode once (replaces upload_machine_bytecode, sp1-gpu/crates/zerocheck/src/prover.rs).
 // blob words: [n_chips] then per chip: main_w prep_w n_constraints n_regs n_instrs n_leaves n_consts n_publics n_asserts,
 // instrs (2 words = one 8-byte DagInstr), leaves (2 words = LeafRef), consts (Montgomery), publics, assert_regs, assert_alphas.
-sp1b200_err sp1b200_machine_create(sp1b200_ctx* ctx, const uint32_t* h_blob, uint64_t n_words, sp1b200_machine** out) {
+sp1b200_err sp1b200_machine_create(sp1b200_ctx* ctx, const uint32_t* h_blob, uint64_t n_words, sp1b200_machine** out) { SP1_DEVICE_GUARD(ctx);
     auto m = std::make_unique<sp1b200_machine>();
     SP1_CUDA(cudaMalloc((void**)&m->d_arena, n_words * 4 + 16));
     SP1_CUDA(cudaMemcpyAsync(m->d_arena, h_blob, n_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t* b = h_blob;
     const uint32_t* end = h_blob + n_words;
     auto dev = [&](const uint32_t* hp) { return m->d_arena + (hp - h_blob); };
+    if (n_words < 1 || !h_blob) return sp1b200_set_error("machine_create: empty blob");
     uint32_t n = *b++;
     for (uint32_t c = 0; c < n; c++) {
-        if (b + 9 > end) return sp1b200_set_error("machine_create: truncated blob");
+        if ((uint64_t)(end - b) < 9) return sp1b200_set_error("machine_create: truncated blob (header of chip %u)", c);
         ChipProg p{}; HostProg hp;
         p.main_w = *b++; p.prep_w = *b++; p.n_constraints = *b++; p.n_regs = *b++;
-        uint32_t ni = *b++, nl = *b++, nc = *b++, np = *b++, na = *b++;
-        if ((uintptr_t)(b - h_blob) % 2 != 0) { /* 8-byte alignment of the instruction stream inside the arena */ }
-        if (b + 2 * ni + 2 * nl + nc + np + 2 * na > end) return sp1b200_set_error("machine_create: truncated blob (chip %u)", c);
-        p.n_instrs = ni; p.n_asserts = na;
+        const uint64_t ni = *b++, nl = *b++, nc = *b++, np = *b++, na = *b++;
+        // all size arithmetic in 64 bits against the words that are left (a 32-bit sum could wrap past the check)
+        if (2 * ni + 2 * nl + nc + np + 2 * na > (uint64_t)(end - b)) return sp1b200_set_error("machine_create: truncated blob (chip %u)", c);
+        if (p.n_regs > 65536) return sp1b200_set_error("machine_create: chip %u declares %u registers (16-bit register indices)", c, p.n_regs);
+        p.n_instrs = (uint32_t)ni; p.n_asserts = (uint32_t)na;
         p.instrs = reinterpret_cast<const DagInstr*>(dev(b)); hp.instrs.resize(ni); memcpy(hp.instrs.data(), b, ni * 8); b += 2 * ni;
         p.leaves = reinterpret_cast<const LeafRef*>(dev(b)); hp.leaves.resize(nl); memcpy(hp.leaves.data(), b, nl * 8); b += 2 * nl;
         p.consts = dev(b); hp.consts.assign(b, b + nc); b += nc;
         p.publics = dev(b); hp.publics.assign(b, b + np); b += np;
         p.assert_regs = dev(b); hp.assert_regs.assign(b, b + na); b += na;
         p.assert_alphas = dev(b); hp.assert_alphas.assign(b, b + na); b += na;
-        for (auto& in : hp.instrs) if (in.out >= p.n_regs && p.n_regs) return sp1b200_set_error("machine_create: register out of range in chip %u", c);
+        // a blob exported for a different chip set must become an error, not an out-of-bounds read on host or device
+        for (const LeafRef& l : hp.leaves) {
+            if (l.source != LEAF_MAIN && l.source != LEAF_PREP) return sp1b200_set_error("machine_create: chip %u: leaf source %u (expected 2 = preprocessed or 4 = main)", c, l.source);
+            if (l.col >= (l.source == LEAF_MAIN ? p.main_w : p.prep_w)) return sp1b200_set_error("machine_create: chip %u: leaf column %u outside the %s width", c, l.col, l.source == LEAF_MAIN ? "main" : "preprocessed");
+        }
+        for (size_t k = 0; k < hp.instrs.size(); k++) {
+            const DagInstr& in = hp.instrs[k];
+            if (in.out >= p.n_regs) return sp1b200_set_error("machine_create: chip %u instr %zu: output register %u >= n_regs %u", c, k, in.out, p.n_regs);
+            bool ok = true;
+            switch (in.opcode) {
+                case BC_LOAD_LEAF: ok = in.a < nl; break;
+                case BC_LOAD_CONST: ok = in.a < nc; break;
+                case BC_LOAD_PUBLIC: ok = in.a < np; break;
+                case BC_ADD_F: case BC_SUB_F: case BC_MUL_F: ok = in.a < p.n_regs && in.b < p.n_regs; break;
+                case BC_NEG_F: ok = in.a < p.n_regs; break;
+                default: return sp1b200_set_error("machine_create: chip %u instr %zu: unknown opcode %u", c, k, in.opcode);
+            }
+            if (!ok) return sp1b200_set_error("machine_create: chip %u instr %zu: operand out of range (opcode %u, a %u, b %u)", c, k, in.opcode, in.a, in.b);
+        }
+        for (size_t k = 0; k < hp.assert_regs.size(); k++) {
+            if (hp.assert_regs[k] >= p.n_regs) return sp1b200_set_error("machine_create: chip %u assert %zu: register %u >= n_regs %u", c, k, hp.assert_regs[k], p.n_regs);
+            if (hp.assert_alphas[k] >= p.n_constraints) return sp1b200_set_error("machine_create: chip %u assert %zu: alpha index %u >= n_constraints %u", c, k, hp.assert_alphas[k], p.n_constraints);
+        }
         m->chips.push_back(p); m->host.push_back(std::move(hp));
     }
     m->interactions = sp1b200_parse_interactions(b, end, n);
@@ -408,9 +432,12 @@ uint32_t sp1b200_machine_num_chips(const sp1b200_machine* m) { return (uint32_t)
 sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const uint64_t* h_heights, const uint32_t* const* d_main,
                               const uint32_t* const* d_prep, const uint32_t* h_pv, uint32_t n_pv, const uint32_t* h_gkr_point,
                               const uint32_t* h_alpha, const uint32_t* h_gamma, const uint32_t* h_claims, uint32_t* h_chal, uint32_t* h_out,
-                              uint64_t cap, uint64_t* h_words) {
+                              uint64_t cap, uint64_t* h_words) { SP1_DEVICE_GUARD(ctx);
     const uint32_t mlr = ctx->params.max_log_row_count;
     const size_t nchips = m->chips.size();
+    for (size_t k = 0; k < nchips; k++)
+        for (uint32_t pi : m->host[k].publics)
+            if (pi >= n_pv) return sp1b200_set_error("zerocheck: chip %zu reads public value %u but only %u were passed", k, pi, n_pv);
     cudaStream_t st = ctx->stream;
     DevFree mem(ctx);
     HostChallenger ch;

@@ -84,14 +84,9 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_baseline(workload_name, target_seconds=20.0):
-    """The oracle port (oracle/liboracle.so, OpenMP over the host cores) proving a BOUNDED sample of the same workload:
-    the same synthetic machine with every chip height scaled down (whole prove_shard body, verifier skipped)."""
-    from tests import oracle_lib as O
-    from sp1_b200 import synth_air as SA
-    L = O.lib()
-    # one OpenMP thread per physical core this process may use: launchers such as torchrun export OMP_NUM_THREADS=1, and two
-    # threads per core (SMT) measured 5x slower on the oracle's barrier-heavy loops (1.2 k vs 6.5 k cycles/s on the GPU box)
+def _oracle_threads(L):
+    """one OpenMP thread per physical core this process may use: launchers such as torchrun export OMP_NUM_THREADS=1, and two
+    threads per core (SMT) measured 5x slower on the oracle's barrier-heavy loops"""
     try:
         ncpu = len(os.sched_getaffinity(0))
         try:
@@ -102,47 +97,179 @@ def cpu_baseline(workload_name, target_seconds=20.0):
         L.orc_set_num_threads(max(1, ncpu // smt))
     except (AttributeError, OSError):
         pass
-    cores = L.orc_num_threads()
+    return int(L.orc_num_threads())
+
+
+class OracleShard:
+    """One synthetic shard (same machine, same chip heights as the GPU arm when scale == 1) set up for the CPU oracle:
+    traces generated once (not timed); prove() = setup commit + the whole prove_shard_with_data body, verifier skipped."""
+
+    def __init__(self, workload_name, scale=1.0):
+        from tests import oracle_lib as O
+        from sp1_b200 import synth_air as SA
+        self.O, self.L = O, O.lib()
+        self.cores = _oracle_threads(self.L)
+        self.mach = W.synthetic_machine(workload_name, seed=42, scale=scale)
+        rng = np.random.default_rng(7)
+        self.mains, self.preps = [], []
+        for h, g, wp in self.mach["specs"]:
+            m_, p_ = SA.synth_trace(rng, h, g, wp, 12345)
+            self.mains.append(m_); self.preps.append(p_)
+        self.pv = O.to_monty(np.array([12345, 5, 6, 7]))
+        self.cells = W.area_of(self.mach["main_shapes"])
+        self.cycles = self.cells / W.CELLS_PER_CYCLE
+
+    def prove(self):
+        import ctypes
+        ch = self.O.Challenger()
+        self.L.orc_set_skip_verify(1)
+        t0 = time.time()
+        self.O.prove_shard_verify(self.mach["blob"], [h for h, _, _ in self.mach["specs"]], self.mains, self.preps, self.mach["names"],
+                                  self.pv, 21, 22, ch)
+        wall = time.time() - t0
+        self.L.orc_set_skip_verify(0)
+        t = (ctypes.c_double * 5)()
+        self.L.orc_shard_times(t)
+        return wall, dict(zip(("setup_commit", "main_commit", "logup_gkr", "zerocheck", "jagged_open"), [round(x, 3) for x in t]))
+
+
+CPU_KIND_NOTE = ("oracle C++ port with OpenMP (scalar Montgomery arithmetic, no AVX-512 packing) - a NAIVE port, not the Rust/AVX-512 "
+                 "Plonky3 prover: `cargo` is probed at run time and is absent in this image")
+
+
+def _cargo_probe():
+    import shutil
+    return shutil.which("cargo") is not None
+
+
+def cpu_baseline(workload_name):
+    """cpu_baseline of the GPU arm: the oracle port on the host cores proving a BOUNDED sample of the workload (the same
+    synthetic machine with every chip height scaled down to ~4 M cells; the protocol parameters stay the core ones, so the fixed
+    costs - 2^21-row stacking, 22 sumcheck rounds, grinds, 124 queries - weigh more than in a full shard: same_config is false;
+    the like-for-like figure is the `--impl reference` arm, which proves the full workload)."""
     full = W.synthetic_machine(workload_name, seed=42)
-    scale = (1 << 22) / W.area_of(full["main_shapes"])
-    mach = W.synthetic_machine(workload_name, seed=42, scale=scale)
-    rng = np.random.default_rng(7)
-    mains, preps = [], []
-    for h, g, wp in mach["specs"]:
-        m_, p_ = SA.synth_trace(rng, h, g, wp, 12345)
-        mains.append(m_); preps.append(p_)
-    pv = O.to_monty(np.array([12345, 5, 6, 7]))
-    ch = O.Challenger()
-    L.orc_set_skip_verify(1)
-    t0 = time.time()
-    O.prove_shard_verify(mach["blob"], [h for h, _, _ in mach["specs"]], mains, preps, mach["names"], pv, 21, 22, ch)
-    wall = time.time() - t0
-    L.orc_set_skip_verify(0)
-    cells = W.area_of(mach["main_shapes"])
-    return {"value": cells / W.CELLS_PER_CYCLE / wall, "unit": "cycles/s", "cores": int(cores), "kind": "port",
-            "sample": f"same machine, heights scaled to {cells} main cells ({cells / W.CELLS_PER_CYCLE:.0f} cycles): whole shard proof "
-                      f"(setup commit + prove_shard body) in {wall:.1f}s; oracle C++ port with OpenMP - not the Rust/AVX-512 "
-                      "Plonky3 prover (cargo absent in this image)"}
+    sh = OracleShard(workload_name, scale=(1 << 22) / W.area_of(full["main_shapes"]))
+    wall, phases = sh.prove()
+    return {"value": sh.cycles / wall, "unit": "cycles/s", "cores": sh.cores, "kind": "port", "same_config": False,
+            "cargo_present": _cargo_probe(), "phases_s": phases,
+            "sample": f"same machine, heights scaled to {sh.cells} main cells ({sh.cycles:.0f} cycles): whole shard proof "
+                      f"(setup commit + prove_shard body) in {wall:.1f}s; {CPU_KIND_NOTE}"}
 
 
 def run_reference(args):
+    """CPU arm, like for like: the oracle port proves the SAME workload as the GPU arm (same machine, same chip heights, core
+    parameters) on all host cores.  One step = one whole shard proof; the arm times as many steps as fit a wall budget (at least 2,
+    at most --steps) and reports the median, the spread, and how many steps it actually timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    cb = None
-    for _ in range(max(1, min(args.steps, 2))):
-        cb = cpu_baseline(args.workload, 10.0)
-        vals.append(cb["value"])
-    v = float(np.mean(vals))
-    cb["value"] = v
+    t_gen = time.time()
+    sh = OracleShard(args.workload, scale=1.0)
+    t_gen = time.time() - t_gen
+    budget = float(os.environ.get("SP1B200_REF_BUDGET_S", "300"))
+    walls, phases = [], None
+    t_start = time.time()
+    while len(walls) < max(1, args.steps):
+        w_, phases = sh.prove()
+        walls.append(w_)
+        if len(walls) >= 2 and time.time() - t_start + float(np.median(walls)) > budget:
+            break
+    med = float(np.median(walls))
+    v = sh.cycles / med
+    cb = {"value": v, "unit": "cycles/s", "cores": sh.cores, "kind": "port", "same_config": True, "cargo_present": _cargo_probe(),
+          "phases_s": phases,
+          "sample": f"the full {args.workload} shard ({sh.cells} main cells = {sh.cycles:.0f} cycles), {len(walls)} timed proofs: "
+                    f"median {med:.1f}s, min {min(walls):.1f}s, max {max(walls):.1f}s; {CPU_KIND_NOTE}"}
     print(json.dumps({"impl": "reference", "metric": "riscv_cycles_proven_per_second_core", "value": v, "unit": "cycles/s",
-                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                      "n_gpus": args.gpus, "steps": len(walls), "steps_requested": args.steps, "warmup": 0, "warmup_requested": args.warmup,
+                      "ms_per_step": med * 1e3, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "u32 KoalaBear (Montgomery) / ext4", "data": "synthetic",
-                      "config": {"workload": f"{args.workload} chip mix, bounded sample", "phases": PHASES_DONE,
-                                 "phases_not_yet_in_step": PHASES_MISSING},
-                      "cpu_baseline": cb,
+                      "config": workload_config(args.workload, sh.cells, sh.cycles, len(sh.mach["specs"]), default_inflight(args)),
+                      "cpu_baseline": cb, "spread": {"min_s": min(walls), "max_s": max(walls), "median_s": med, "n": len(walls)},
+                      "trace_generation_s": round(t_gen, 1),
                       "e2e": {"value": v, "unit": "cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def default_inflight(args):
+    """shards proven concurrently per GPU: as many as the device memory comfortably holds (measured: ~17-24 GB per S2 context at the
+    pool's high water mark; throughput saturates at 5-6 contexts), never more than 5"""
+    return args.inflight if args.inflight > 0 else {"S1": 5, "S2": 5, "S3": 3}.get(args.workload, 3)
+
+
+def workload_config(workload, cells, cycles, n_chips, inflight):
+    """the `config` object both arms print"""
+    padded = ((cells + (1 << 21) - 1) >> 21) << 21
+    c = {"workload": f"{workload}: {W.WORKLOADS[workload][1]}; main area {cells} cells = {cycles:.0f} cycles/shard "
+                     f"(cells/45), {n_chips} chips (synthetic AIR bytecode + LogUp interactions), {padded >> 21} stacked columns of 2^21, blowup 4, "
+                     f"124 queries, 16+5+12 PoW bits",
+         "phases": PHASES_DONE, "phases_not_yet_in_step": PHASES_MISSING}
+    # identical in both arms (the driver compares the two config objects): the GPU-arm notes are stated for the GPU arm
+    c["inflight"] = f"GPU arm: {inflight} shard(s) in flight per GPU per step (one context + stream each); CPU arm: one shard at a time on all host cores"
+    c["l2"] = "GPU arm: working set (>= 3 GB codeword per shard) exceeds the 126 MB L2 between iterations"
+    return c
+
+
+def ref_kernels_leg(lib, n_cols, dev):
+    """Head to head on this box: the REFERENCE's own CUDA kernels (oracle/_ref, compiled unmodified from sp1-gpu/crates/sys; launch
+    shapes of its Rust host code) against this library's kernel-level entry points, on identical device buffers of the S2 commit
+    shape.  Outside every timed region; a checker-side measurement, never part of the product path.  ratio = ref_ms / repo_ms."""
+    import ctypes as C
+    import torch
+    from tests import ref_lib as R
+    if not R.available():
+        return {"unavailable": "oracle/_ref/libsp1ref.so not built"}
+    R.lib()
+
+    class TB:  # torch tensor seen as a device buffer by the reference launcher
+        def __init__(self, t):
+            self.t = t; self.ptr = C.c_void_p(t.data_ptr())
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    out = {}
+    log_h, lb = 21, 2
+    msg = torch.randint(0, W.P, (n_cols, 1 << log_h), dtype=torch.int32, device=dev, generator=g)
+    cw_ref = torch.empty((n_cols, 1 << (log_h + lb)), dtype=torch.int32, device=dev)
+    cw = torch.empty_like(cw_ref)
+    torch.cuda.synchronize()
+
+    def best(fn, reps=3):
+        v = []
+        for _ in range(reps):
+            v.append(fn())
+        return min(v)
+    # RS-encode
+    ref_ms = best(lambda: R.batch_coset_dft(None, lb, d_in=TB(msg), d_out=TB(cw_ref), shape=(n_cols, 1 << log_h))[1])
+
+    def mine_rs():
+        lib.rs_encode(msg, cw, n_cols, log_h, lb); lib.sync()
+        return lib.phase_ms("rs_encode")
+    my_ms = best(mine_rs)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(cw, cw_ref))
+    out["rs_encode"] = {"shape": f"{n_cols} cols 2^21 -> 2^23", "ref_ms": ref_ms, "repo_ms": my_ms, "ratio": ref_ms / my_ms, "bit_identical": same}
+    del cw_ref
+    # Merkle: leaf hash + compress layers over the codeword
+    h = log_h + lb
+    nd = (2 << h) - 1
+    dg_ref = torch.empty(nd * 8, dtype=torch.int32, device=dev)
+    dg = torch.empty(nd * 8, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    r_leaf, r_comp = 1e30, 1e30
+    for _ in range(3):
+        _, (a_, b_) = R.merkle_tree((n_cols, 1 << h), d_mat=TB(cw), d_digests=TB(dg_ref))
+        r_leaf, r_comp = min(r_leaf, a_), min(r_comp, b_)
+    m_leaf, m_tot = 1e30, 1e30
+    for _ in range(3):
+        root, _c = lib.merkle_commit(cw, n_cols, h, d_layers=dg); lib.sync()
+        m_leaf, m_tot = min(m_leaf, lib.phase_ms("merkle.leaf_hash")), min(m_tot, lib.phase_ms("merkle_commit"))
+    torch.cuda.synchronize()
+    root_ref = dg_ref[:8].cpu().numpy().view(np.uint32)
+    out["leaf_hash"] = {"shape": f"{n_cols} cols x 2^23 rows", "ref_ms": r_leaf, "repo_ms": m_leaf, "ratio": r_leaf / m_leaf}
+    out["compress_tree"] = {"shape": "2^23 leaves, 23 layers", "ref_ms": r_comp, "repo_ms": m_tot - m_leaf, "ratio": r_comp / (m_tot - m_leaf),
+                            "root_identical": bool((root_ref == root).all())}
+    out["note"] = ("reference kernels: leafHashPacked + compress (sys/lib/merkle_tree/merkle_tree.cu:27-94, launch shapes of "
+                   "merkle_tree/src/single_layer.rs:109-150), batch_coset_dft (sys/include/ntt/sppark.cuh:49-107); CUDA events, best of 3; "
+                   "repo compress_tree = merkle_commit - leaf_hash phases")
+    return out
 
 
 def main():
@@ -153,6 +280,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="S2", choices=list(W.WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-kernels", action="store_true", help="skip the head-to-head timing of the reference's own CUDA kernels (oracle/_ref)")
     ap.add_argument("--inflight", type=int, default=0,
                     help="shards proven concurrently per GPU (one library context + stream + host thread each): the latency-bound "
                          "sumcheck tails of one shard overlap the NTT / Poseidon2 kernels of another")
@@ -208,8 +336,7 @@ def main():
     # further in-flight provers on the same GPU: own context (stream, mailbox, upload slots), own machine / preprocessed commit
     # default: as many shards in flight as the device memory comfortably holds (measured: ~24 GB per S2 context at the pool's high
     # water mark; throughput saturates at 5-6 contexts), never more than 5
-    if args.inflight <= 0:
-        args.inflight = {"S1": 5, "S2": 5, "S3": 3}.get(args.workload, 3)
+    args.inflight = default_inflight(args)
     provers = [(lib, machine, h_prep)]
     for _ in range(1, args.inflight):
         l2 = Lib(device=local)
@@ -319,11 +446,7 @@ def main():
         "metric": "riscv_cycles_proven_per_second_core", "value": value, "unit": "cycles/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 KoalaBear (Montgomery) / ext4", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {W.WORKLOADS[args.workload][1]}; main area {cells} cells = {cycles:.0f} cycles/shard "
-                               f"(cells/45), {len(specs)} chips (synthetic AIR bytecode + LogUp interactions), {padded_cells >> 21} stacked columns of 2^21, blowup 4, "
-                               f"124 queries, 16+5 PoW bits; {len(provers)} shard(s) in flight per GPU per step (one context + stream each)",
-                   "phases": PHASES_DONE, "phases_not_yet_in_step": PHASES_MISSING,
-                   "l2": "working set (>= 3 GB codeword per shard) exceeds the 126 MB L2 between iterations"},
+        "config": workload_config(args.workload, cells, cycles, len(specs), len(provers)),
         "e2e": {"value": e2e, "unit": "cycles/s", "h2d_bytes_per_step": int(cells * 4) * len(provers), "d2h_bytes_per_step": int(proof_bytes) * len(provers),
                 "ms_per_step": ms_e2e / args.steps,
                 "note": "host trace in pinned memory -> sp1b200_upload_begin (two device slots, copy stream) -> sp1b200_prove_shard; "
@@ -351,17 +474,27 @@ def main():
         "poseidon2": {"leaf+compress_perms_per_step": int(perms), "gperm_per_s": perms / (merkle_ms / 1e3) / 1e9,
                       "note": "INT32-ALU bound (see DESIGN.md), not HBM bound"},
     }
+    for l_, m_, p_ in provers[1:]:
+        l_.jagged_round_free(p_)
+        l_.machine_free(m_)
+        l_.close()
+    del d_main, h_main
+    torch.cuda.empty_cache()
     if rank == 0:
+        if world == 1 and not args.no_ref_kernels:
+            try:
+                out["vs_ref_kernels"] = ref_kernels_leg(lib, int(n_stacked), dev)
+            except Exception as e:  # the reference kernels are a checker-side bar; the GPU numbers stand without them
+                out["vs_ref_kernels"] = {"unavailable": f"failed: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 out["cpu_baseline"] = cpu_baseline(args.workload)
             except Exception as e:  # the oracle is a checker; the GPU numbers stand without it
                 out["cpu_baseline"] = {"value": None, "unit": "cycles/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(out))
-    for l_, m_, p_ in provers:
-        l_.jagged_round_free(p_)
-        l_.machine_free(m_)
-        l_.close()
+    lib.jagged_round_free(h_prep)
+    lib.machine_free(machine)
+    lib.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -79,6 +79,13 @@ extern "C" {
 
 // bench.py cpu_baseline support: skip the (restated) verifier and report the phase times of the last jagged run
 void orc_set_skip_verify(int v) { g_skip_verify = v; }
+// tests only: make every grind return its (skip+1)-th smallest valid witness; the witnesses found are logged in grind order
+void orc_set_grind_skip(uint32_t skip) { Challenger::grind_skip() = skip; Challenger::witness_log().clear(); }
+uint32_t orc_witness_log(uint32_t* out, uint32_t cap) {
+    auto& l = Challenger::witness_log();
+    for (uint32_t i = 0; i < l.size() && i < cap; i++) out[i] = l[i];
+    return (uint32_t)l.size();
+}
 void orc_last_times(double* out4) { for (int i = 0; i < 4; i++) out4[i] = g_times[i]; }
 static double g_shard_times[5] = {0, 0, 0, 0, 0};  // seconds of the last orc_prove_shard_verify: prep commit, main commit, LogUp-GKR, zerocheck, jagged/BaseFold open
 void orc_shard_times(double* out5) { for (int i = 0; i < 5; i++) out5[i] = g_shard_times[i]; }

@@ -149,11 +149,21 @@ struct Challenger {
     bool check_witness(unsigned bits, F w) { observe(w); return sample_bits(bits) == 0; }
     // canonical-min mode: smallest canonical witness (deterministic; the reference returns ANY valid
     // witness: p3 DuplexChallenger::grind uses a parallel find_any)
+    // grind_skip() > 0 (tests only): return the (skip+1)-th smallest valid witness instead - a deliberately NON-minimal witness, as a
+    // racing reference prover may return; the product must reproduce the resulting proof in replay mode (grind_mode = 1).
+    static unsigned& grind_skip() { static unsigned s = 0; return s; }
+    static std::vector<uint32_t>& witness_log() { static std::vector<uint32_t> l; return l; }   // Montgomery words, in grind order
     F grind(unsigned bits) {
+        unsigned skip = grind_skip();
         for (uint32_t w = 0; w < KB_P; w++) {
             Challenger c = *this;
             F wf = F::from_canonical(w);
-            if (c.check_witness(bits, wf)) { bool ok = check_witness(bits, wf); assert(ok); (void)ok; return wf; }
+            if (c.check_witness(bits, wf)) {
+                if (skip) { skip--; continue; }
+                bool ok = check_witness(bits, wf); assert(ok); (void)ok;
+                witness_log().push_back(wf.v);
+                return wf;
+            }
         }
         assert(false && "no PoW witness");
         return F::zero();

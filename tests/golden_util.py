@@ -39,3 +39,29 @@ def check_words(case, prep_commit, words, final_state):
         off += ln
     assert hashlib.sha256(words.astype("<u4").tobytes()).hexdigest() == case["sha256"], "proof words differ from the golden fixture"
     assert [int(x) for x in final_state] == case["final_challenger"], "final challenger state differs from the golden fixture"
+
+
+# ---- BASELINE-size goldens (tests/golden/shard_proofs_fullsize.json): workloads S1 / S2 with the core protocol parameters ------------
+FULL_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shard_proofs_fullsize.json")
+FULL_PV0 = 12345
+
+
+def fullsize_cases():
+    return json.load(open(FULL_PATH))["cases"] if os.path.exists(FULL_PATH) else []
+
+
+def fullsize_inputs(workload, seed):
+    """the seeded full-size inputs of a golden case: the bench machine of `workload` (sp1_b200.workload.synthetic_machine) with numpy
+    traces (so that the CPU generator and the GPU test see the same words).  -> (mach, heights, mains, preps, pv, challenger)"""
+    from sp1_b200 import synth_air as SA
+    from sp1_b200 import workload as W
+    mach = W.synthetic_machine(workload, seed=42)
+    rng = np.random.default_rng(seed)
+    mains, preps = [], []
+    for h, g, wp in mach["specs"]:
+        m_, p_ = SA.synth_trace(rng, h, g, wp, FULL_PV0)
+        mains.append(m_); preps.append(p_)
+    pv = O.to_monty(np.array([FULL_PV0, 5, 6, 7]))
+    ch = O.Challenger()
+    ch.observe(O.rand_field(rng, 9))
+    return mach, [h for h, _, _ in mach["specs"]], mains, preps, pv, ch

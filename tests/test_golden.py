@@ -35,3 +35,14 @@ def test_verify_only_accepts_oracle_proofs_and_rejects_tampering(case):
         assert O.verify_shard(blob, heights, names, case["log_stacking_height"], case["max_log_row_count"], v, pc, bad, **kw) != 0
         off += ln
     assert O.verify_shard(blob, heights, names, case["log_stacking_height"], case["max_log_row_count"], start.clone(), pc, words[:-1], **kw) == -2
+
+
+def test_baseline_size_goldens_are_committed_with_core_parameters():
+    """tests/golden/shard_proofs_fullsize.json (tools/gen_golden_proofs.py --full S1 S2): proving them again takes minutes of CPU, so
+    the CPU suite only checks the fixtures' shape; the GPU suite reproduces them bit for bit (tests/test_gpu_golden.py)."""
+    cases = {c["name"]: c for c in G.fullsize_cases()}
+    assert {"S1", "S2"} <= set(cases)
+    for c in cases.values():
+        assert (c["log_stacking_height"], c["max_log_row_count"], c["num_queries"], c["pow_bits"], c["batch_pow_bits"], c["gkr_pow_bits"]) == \
+               (21, 22, 124, 16, 5, 12)
+        assert len(c["sha256"]) == 64 and len(c["final_challenger"]) == 34 and sum(c["section_lengths"]) + 6 == c["n_words"]

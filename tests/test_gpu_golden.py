@@ -28,3 +28,23 @@ def test_gpu_reproduces_golden_shard_proofs(case):
         lib.jagged_round_free(prep_round)
     lib.machine_free(mach)
     lib.close()
+
+
+@pytest.mark.parametrize("case", G.fullsize_cases(), ids=lambda c: c["name"])
+def test_gpu_reproduces_baseline_size_golden(case):
+    """BASELINE-size bit parity (workloads S1 / S2, CORE protocol parameters): the code paths that only run at scale (fast RS-encode
+    tiles, flat compress layers above 2^16, zerocheck pieces, 96-job GKR batches) against the oracle's committed proof."""
+    from sp1_b200 import Lib
+    mach, heights, mains, preps, pv, ch = G.fullsize_inputs(case["workload"], case["seed"])
+    lib = Lib(0)   # sp1b200_default_core_params
+    m = lib.machine_create(mach["blob"])
+    prep_tabs = [p for p in preps if p is not None]
+    pc, prep_round = lib.jagged_commit(prep_tabs)
+    dense = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(x).reshape(-1) for x in mains if x.size]))
+    del mains
+    st = ch.st.copy()
+    words = lib.prove_shard(m, prep_round, dense, heights, mach["names"], pv, st)
+    G.check_words(case, pc, words, st)
+    lib.jagged_round_free(prep_round)
+    lib.machine_free(m)
+    lib.close()

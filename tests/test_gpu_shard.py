@@ -77,3 +77,48 @@ def test_prove_shard_from_upload_slots_is_identical():
     lib.jagged_round_free(prep_round)
     lib.machine_free(mach)
     lib.close()
+
+
+@pytest.mark.parametrize("skip", [1, 3])
+def test_prove_shard_replays_non_minimal_witnesses(skip):
+    """Whole-shard replay mode (grind_mode = 1) with deliberately NON-minimal witnesses: the oracle grinds the (skip+1)-th smallest
+    valid witness at each of the three sites (as a racing reference prover may), the product replays exactly those three witnesses
+    and must reproduce every proof word and the final challenger state — the mode used to cross-sign against a Rust-made proof."""
+    import ctypes as C
+    from sp1_b200 import Lib
+    spec = [(1024, 2, True), (256 + 32, 3, False), (0, 1, False), (2048, 1, True)]
+    log_stack, mlr, nq, pw, bpw, gpw = 10, 11, 8, 4, 2, 3
+    rng = np.random.default_rng(5150 + skip)
+    blob, heights, mains, preps, pv = _synth_machine_gkr(rng, spec)
+    names = [f"Chip{i:02d}" for i in range(len(heights))]
+    ch = O.Challenger(); ch.observe(O.rand_field(rng, 9))
+    L = O.lib()
+    omin = ch.clone()
+    _, wmin = O.prove_shard_verify(blob, heights, mains, preps, names, pv, log_stack, mlr, omin, num_queries=nq, pow_bits=pw,
+                                   batch_pow_bits=bpw, gkr_pow_bits=gpw)
+    L.orc_set_grind_skip(C.c_uint32(skip))
+    try:
+        och = ch.clone()
+        opc, owords = O.prove_shard_verify(blob, heights, mains, preps, names, pv, log_stack, mlr, och, num_queries=nq, pow_bits=pw,
+                                           batch_pow_bits=bpw, gkr_pow_bits=gpw)
+        wl = np.zeros(8, np.uint32)
+        n = L.orc_witness_log(O.ptr(wl), C.c_uint32(8))
+    finally:
+        L.orc_set_grind_skip(C.c_uint32(0))
+    assert n == 3, "the shard proof has three grinding sites: LogUp-GKR, BaseFold batching, BaseFold queries"
+    assert owords.size == wmin.size and (owords != wmin).any(), "non-minimal witnesses must change the proof"
+    lib = Lib(0, log_stacking_height=log_stack, max_log_row_count=mlr, num_queries=nq, pow_bits=pw, batch_pow_bits=bpw, gkr_pow_bits=gpw,
+              grind_mode=1)
+    mach = lib.machine_create(blob)
+    pc, prep_round = lib.jagged_commit([p for p in preps if p is not None])
+    assert (pc == opc).all()
+    dense = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(m).reshape(-1) for m in mains if m.size]))
+    st = ch.st.copy()
+    words = lib.prove_shard(mach, prep_round, dense, heights, names, pv, st, replay=wl[:3])
+    assert words.size == owords.size
+    bad = np.nonzero(words != owords)[0]
+    assert bad.size == 0, f"first differing words {bad[:8]} of {words.size}"
+    assert (st == och.st).all()
+    lib.jagged_round_free(prep_round)
+    lib.machine_free(mach)
+    lib.close()

@@ -54,7 +54,48 @@ def run_case(name, spec, log_stack, mlr, seed, nq, pw, bpw, gpw):
     }
 
 
+def summarize(name, pc, words, ch, extra):
+    n_sec = int(words[0])
+    lens = [int(x) for x in words[1:1 + n_sec]]
+    off = 1 + n_sec
+    heads = []
+    for ln in lens:
+        sec = words[off:off + ln]
+        heads.append({"first": [int(x) for x in sec[:8]], "last": [int(x) for x in sec[-8:]]})
+        off += ln
+    d = {"name": name, "prep_commit": [int(x) for x in pc], "main_commit": [int(x) for x in words[1 + n_sec:1 + n_sec + 8]],
+         "final_challenger": [int(x) for x in ch.st], "section_lengths": lens, "n_words": int(words.size),
+         "sha256": hashlib.sha256(words.astype("<u4").tobytes()).hexdigest(), "sections": heads}
+    d.update(extra)
+    return d
+
+
+def full_size(workloads):
+    """BASELINE-size goldens: the bench workloads with the CORE protocol parameters (2^21 stacking, 2^22 rows, 124 queries, 16+5+12 PoW
+    bits), proven once by the oracle (minutes on 8 cores) -> tests/golden/shard_proofs_fullsize.json.  Also stores the three grinding
+    witnesses so that the replay-mode test can reproduce the same proof with grind_mode = 1."""
+    import time
+    from tests import golden_util as G
+    path = G.FULL_PATH
+    old = {c["name"]: c for c in (json.load(open(path))["cases"] if os.path.exists(path) else [])}
+    for wl in workloads:
+        seed = 9000 + sum(ord(c) for c in wl)
+        mach, heights, mains, preps, pv, ch = G.fullsize_inputs(wl, seed)
+        t0 = time.time()
+        pc, words = O.prove_shard_verify(mach["blob"], heights, mains, preps, mach["names"], pv, 21, 22, ch)
+        print(f"{wl}: oracle proved + verified in {time.time() - t0:.0f}s, {words.size} words", flush=True)
+        old[wl] = summarize(wl, pc, words, ch, {"workload": wl, "seed": seed, "log_stacking_height": 21, "max_log_row_count": 22,
+                                                "num_queries": 124, "pow_bits": 16, "batch_pow_bits": 5, "gkr_pow_bits": 12})
+    out = {"generator": "tools/gen_golden_proofs.py --full (oracle/liboracle.so incl. its restated verifier; minimum-witness grinding)",
+           "cases": [old[k] for k in sorted(old)]}
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", path, [c["sha256"][:12] for c in out["cases"]])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--full":
+        return full_size(sys.argv[2:] or ["S1"])
     out = {"generator": "tools/gen_golden_proofs.py (oracle/liboracle.so; minimum-witness grinding)",
            "format": "proof words = [n_sections][lengths] then main commitment | LogUp-GKR | zerocheck + opened values | evaluation proof | "
                      "public values; u32 little-endian for the hash",

@@ -124,6 +124,154 @@ template <> struct Var<10> { static constexpr const char* name = "product sbox, 
 template <> struct Var<11> { static constexpr const char* name = "product sbox, partial x4, full x2"; static __device__ void f(uint32_t (&s)[16]) { u::p4f2(s); } };
 template <> struct Var<12> { static constexpr const char* name = "product sbox, partial x20"; static __device__ void f(uint32_t (&s)[16]) { u::p20f1(s); } };
 
+
+// ---- round-2 variants ----------------------------------------------------------------------------------------------------
+namespace w {
+using kb::P;
+constexpr uint32_t MU = 0x81000001u;  // +p^-1 mod 2^32
+// s-box with the Montgomery quotient taken from ONE pre-multiplied operand: x' = x * p^-1 (mod 2^32) serves both products
+// (m = lo(a x) p^-1 = a x' mod 2^32), so no low half of a product is ever formed: IMAD x3 + IMAD.HI x4 instead of IMAD x4 + IMAD.HI x4.
+__device__ __forceinline__ uint32_t sbox_pre(uint32_t s, uint32_t rc) {
+    const uint32_t x = kb::add(s, rc);
+    const uint32_t xp = x * MU;
+    const uint32_t x2 = __umulhi(x, x) - __umulhi(x * xp, P) + P;      // (0, 2p)
+    const uint32_t r = __umulhi(x2, x) - __umulhi(x2 * xp, P);        // x2 x < 2 p^2 < 2^32 p  ->  (-p, p)
+    return kb::umin(r, r + P);
+}
+// internal layer with the lane shift folded into the quotient constant: lo(x << k) p^-1 = x (p^-1 << k) mod 2^32
+__device__ __forceinline__ void int_layer_fold(uint32_t (&s)[16]) {
+    uint64_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) sum += s[i];
+    const uint32_t slo = (uint32_t)sum, shi = (uint32_t)(sum >> 32);
+    const uint32_t r = shi - __umulhi(slo * MU, P);
+    const uint32_t sigma = kb::umin(r, r + P);
+    const uint32_t sigma_p = sigma + P;
+    const uint32_t q0 = __umulhi(s[0] * MU, P);
+    const uint32_t y0 = kb::add(sigma, kb::add(q0, q0));
+    s[1] = sigma_p - __umulhi(s[1] * MU, P);
+#pragma unroll
+    for (int i = 2; i < 16; i++) {
+        const int k = (i == 15) ? 15 : (i - 1);
+        s[i] = sigma_p + (s[i] >> (32 - k)) - __umulhi(s[i] * (MU << k), P);
+    }
+    s[0] = y0;
+}
+template <int SB, int IL>
+__device__ __forceinline__ void permute(uint32_t (&s)[16]) {
+    p2::ext_layer(s);
+#pragma unroll 2
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = SB ? sbox_pre(s[i], p2::RC.ext[r * 16 + i]) : p2::sbox(s[i], p2::RC.ext[r * 16 + i]);
+        p2::ext_layer(s);
+    }
+#pragma unroll 4
+    for (int r = 0; r < 20; r++) {
+        s[0] = SB ? sbox_pre(s[0], p2::RC.inr[r]) : p2::sbox(s[0], p2::RC.inr[r]);
+        if (IL) int_layer_fold(s); else p2::int_layer_lazy(s);
+    }
+#pragma unroll
+    for (int i = 1; i < 16; i++) { uint32_t x = s[i]; x = kb::umin(x, x - P); s[i] = kb::umin(x, x - P); }
+#pragma unroll 2
+    for (int r = 4; r < 8; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = SB ? sbox_pre(s[i], p2::RC.ext[r * 16 + i]) : p2::sbox(s[i], p2::RC.ext[r * 16 + i]);
+        p2::ext_layer(s);
+    }
+}
+
+// Warp-cooperative permutation (BASELINE.json's north star asks for it): one lane of the state per thread, two states per warp.
+// Full rounds: one s-box per thread, the 4x4 MDS and the column sums through xor-shuffles; partial rounds: lane 0 of each half-warp
+// runs the s-box, the 16-lane sum is a 4-step butterfly.  `x` is this thread's lane (canonical); l = lane index 0..15.
+__device__ __forceinline__ uint32_t shx(uint32_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ uint32_t coop_ext_layer(uint32_t x, int l) {
+    using namespace kb;
+    // quad sum S = x0+x1+x2+x3 ; out_i = S + x_i + 2 x_{i+1}   (rows of circ(2,3,1,1))
+    const uint32_t a = add(x, shx(x, 1));
+    const uint32_t S = add(a, shx(a, 2));
+    const uint32_t nxt = __shfl_sync(0xffffffffu, x, (threadIdx.x & ~3) | ((l + 1) & 3));
+    const uint32_t y = add(add(S, x), dbl(nxt));
+    // column sums over the four quads, then y += colsum
+    const uint32_t c = add(y, shx(y, 4));
+    const uint32_t C = add(c, shx(c, 8));
+    return add(y, C);
+}
+__device__ __forceinline__ uint32_t coop_permute(uint32_t x, int l) {
+    using namespace kb;
+    x = coop_ext_layer(x, l);
+    for (int r = 0; r < 4; r++) { x = p2::sbox(x, p2::RC.ext[r * 16 + l]); x = coop_ext_layer(x, l); }
+    const int k = (l == 15) ? 15 : (l - 1);
+    for (int r = 0; r < 20; r++) {
+        if (l == 0) x = p2::sbox(x, p2::RC.inr[r]);
+        // sum of the 16 lanes (canonical values < p: pair sums fit 32 bits, then 64-bit halves)
+        uint32_t lo = x, hi = 0;
+#pragma unroll
+        for (int m = 1; m < 16; m <<= 1) {
+            const uint32_t ol = shx(lo, m), oh = shx(hi, m);
+            const uint32_t nl = lo + ol;
+            hi = hi + oh + (nl < lo);
+            lo = nl;
+        }
+        const uint32_t rr = hi - __umulhi(lo * MU, P);
+        const uint32_t sigma = kb::umin(rr, rr + P);
+        uint32_t y;
+        if (l == 0) { const uint32_t q0 = __umulhi(x * MU, P); y = add(sigma, add(q0, q0)); }
+        else if (l == 1) { const uint32_t t = sigma + P - __umulhi(x * MU, P); y = kb::umin(t, t - P); y = kb::umin(y, y - P); }
+        else { uint32_t t = sigma + P + (x >> (32 - k)) - __umulhi(x * (MU << k), P); t = kb::umin(t, t - P); y = kb::umin(t, t - P); }
+        x = y;
+    }
+    for (int r = 4; r < 8; r++) { x = p2::sbox(x, p2::RC.ext[r * 16 + l]); x = coop_ext_layer(x, l); }
+    return x;
+}
+}  // namespace w
+
+template <> struct Var<13> { static constexpr const char* name = "r02: pre-multiplied sbox (x' = x p^-1)"; static __device__ void f(uint32_t (&s)[16]) { w::permute<1, 0>(s); } };
+template <> struct Var<14> { static constexpr const char* name = "r02: shift folded into quotient const"; static __device__ void f(uint32_t (&s)[16]) { w::permute<0, 1>(s); } };
+template <> struct Var<15> { static constexpr const char* name = "r02: both"; static __device__ void f(uint32_t (&s)[16]) { w::permute<1, 1>(s); } };
+
+// warp-cooperative harness: 16 threads per state
+__global__ void __launch_bounds__(256) bench_coop(uint32_t* out, int iters) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = threadIdx.x & 15;
+    uint32_t x = ((t >> 4) * 2654435761u + l * 40503u) % kb::P;
+    for (int it = 0; it < iters; it++) x = w::coop_permute(x, l);
+    out[t] = x;
+}
+__global__ void check_coop(uint32_t* bad) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = threadIdx.x & 15;
+    uint32_t a[16];
+    for (int i = 0; i < 16; i++) { a[i] = ((t >> 4) * 2246822519u + i * 3266489917u) % kb::P; if ((t >> 4) % 7 == 0 && i % 3 == 0) a[i] = kb::P - 1; if ((t >> 4) % 11 == 0) a[i] = 0; }
+    uint32_t x = a[0];
+    for (int i = 0; i < 16; i++) if (i == l) x = a[i];
+    p2::permute(a);
+    x = w::coop_permute(x, l);
+    uint32_t want = a[0];
+    for (int i = 0; i < 16; i++) if (i == l) want = a[i];
+    if (x != want) atomicAdd(bad, 1);
+}
+void run_coop(uint32_t* d_out, int sms) {
+    uint32_t* d_bad; cudaMalloc(&d_bad, 4); cudaMemset(d_bad, 0, 4);
+    check_coop<<<64, 256>>>(d_bad);
+    uint32_t bad; cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost); cudaFree(d_bad);
+    const int iters = 16, blocks = sms * 8 * 4;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    bench_coop<<<blocks, 256>>>(d_out, 2);
+    cudaDeviceSynchronize();
+    float best = 1e9;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        bench_coop<<<blocks, 256>>>(d_out, iters);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, bench_coop);
+    double perms = (double)blocks * 256 / 16 * iters;
+    printf("%-40s %8.3f ms  %6.2f Gperm/s  regs=%d  mismatches=%u\n", "r02: warp-cooperative (16 lanes/state)", best, perms / best * 1e-6, fa.numRegs, bad);
+}
+
 template <int V>
 __global__ void __launch_bounds__(256) bench(uint32_t* out, int iters) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,5 +332,9 @@ int main() {
     run<10>(d_out, pr.multiProcessorCount);
     run<11>(d_out, pr.multiProcessorCount);
     run<12>(d_out, pr.multiProcessorCount);
+    run<13>(d_out, pr.multiProcessorCount);
+    run<14>(d_out, pr.multiProcessorCount);
+    run<15>(d_out, pr.multiProcessorCount);
+    run_coop(d_out, pr.multiProcessorCount);
     return 0;
 }

@@ -112,8 +112,8 @@ class OracleShard:
         self.mach = W.synthetic_machine(workload_name, seed=42, scale=scale)
         rng = np.random.default_rng(7)
         self.mains, self.preps = [], []
-        for h, g, wp in self.mach["specs"]:
-            m_, p_ = SA.synth_trace(rng, h, g, wp, 12345)
+        for h, g, wp, extra in self.mach["specs"]:
+            m_, p_ = SA.synth_trace(rng, h, g, wp, 12345, extra_cols=extra)
             self.mains.append(m_); self.preps.append(p_)
         self.pv = O.to_monty(np.array([12345, 5, 6, 7]))
         self.cells = W.area_of(self.mach["main_shapes"])
@@ -124,7 +124,7 @@ class OracleShard:
         ch = self.O.Challenger()
         self.L.orc_set_skip_verify(1)
         t0 = time.time()
-        self.O.prove_shard_verify(self.mach["blob"], [h for h, _, _ in self.mach["specs"]], self.mains, self.preps, self.mach["names"],
+        self.O.prove_shard_verify(self.mach["blob"], [s_[0] for s_ in self.mach["specs"]], self.mains, self.preps, self.mach["names"],
                                   self.pv, 21, 22, ch)
         wall = time.time() - t0
         self.L.orc_set_skip_verify(0)
@@ -278,7 +278,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="S2", choices=list(W.WORKLOADS))
+    ap.add_argument("--workload", default="S2c", choices=list(W.WORKLOADS),
+                    help="S2c (default): the sha-bench-like 2^22-cycle shard with CALIBRATED chips (constraint counts and LogUp message "
+                         "statistics read off the reference's Rust eval functions, sp1_b200/chip_stats.json); S2: the same shapes with the "
+                         "light round-1 chip template")
+    ap.add_argument("--no-light-line", action="store_true", help="skip the side-by-side run of the light-template workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-kernels", action="store_true", help="skip the head-to-head timing of the reference's own CUDA kernels (oracle/_ref)")
     ap.add_argument("--inflight", type=int, default=0,
@@ -312,14 +316,14 @@ def main():
     my_shard = SH.shards_of_rank(world, rank, world)[0]
     mach = W.synthetic_machine(args.workload, seed=42)
     specs, names = mach["specs"], mach["names"]
-    heights = [h for h, _, _ in specs]
+    heights = [s_[0] for s_ in specs]
     cells = W.area_of(mach["main_shapes"])
     cycles = cells / W.CELLS_PER_CYCLE
     pv0 = 12345
     pv = ((np.array([pv0, 5, 6, 7], dtype=np.uint64) << np.uint64(32)) % np.uint64(W.P)).astype(np.uint32)
     mains, preps = [], []
-    for i, (h, g, wp) in enumerate(specs):
-        m_, p_ = SA.synth_trace_cuda(h, g, wp, pv0, SH.shard_seed(0, my_shard) + i, dev)
+    for i, (h, g, wp, extra) in enumerate(specs):
+        m_, p_ = SA.synth_trace_cuda(h, g, wp, pv0, SH.shard_seed(0, my_shard) + i, dev, extra_cols=extra)
         mains.append(m_)
         if wp:
             preps.append(p_)
@@ -331,7 +335,7 @@ def main():
     torch.cuda.synchronize()
     # setup (not timed; reference: AirProver::setup uploads the machine and commits the preprocessed traces once per program)
     machine = lib.machine_create(mach["blob"])
-    prep_rows = [h for h, _, wp in specs if wp]
+    prep_rows = [s_[0] for s_ in specs if s_[2]]
     _, h_prep = lib.jagged_commit_dense(d_prep, prep_rows, [1] * len(prep_rows))
     # further in-flight provers on the same GPU: own context (stream, mailbox, upload slots), own machine / preprocessed commit
     # default: as many shards in flight as the device memory comfortably holds (measured: ~24 GB per S2 context at the pool's high
@@ -481,6 +485,21 @@ def main():
     del d_main, h_main
     torch.cuda.empty_cache()
     if rank == 0:
+        if world == 1 and not args.no_light_line and args.workload in W.BASE_OF:
+            # side by side: the same shard shapes with the light round-1 chip template, measured by a child process now that this
+            # process has released its shards (same code path, fewer steps; not part of `value`)
+            try:
+                lib.jagged_round_free(h_prep); lib.machine_free(machine); h_prep = machine = None
+                cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", W.BASE_OF[args.workload], "--steps", str(min(args.steps, 5)),
+                                     "--warmup", "3", "--no-cpu-baseline", "--no-ref-kernels", "--no-light-line", "--inflight", str(args.inflight)],
+                                    capture_output=True, text=True, timeout=600)
+                lj = json.loads(cp.stdout.strip().splitlines()[-1])
+                out["light_workload"] = {"workload": lj["config"]["workload"], "value": lj["value"], "e2e": lj["e2e"]["value"], "unit": "cycles/s",
+                                         "ms_per_shard": lj["ms_per_shard"], "kernels_ms_per_shard_alone": lj["kernels_ms_per_shard_alone"],
+                                         "note": "same shard shapes, light chip template (round-1 headline workload): ~4 constraints per 6 columns, "
+                                                 "1-3 values per interaction on a third of the column groups"}
+            except Exception as e:
+                out["light_workload"] = {"unavailable": f"failed: {e}"}
         if world == 1 and not args.no_ref_kernels:
             try:
                 out["vs_ref_kernels"] = ref_kernels_leg(lib, int(n_stacked), dev)
@@ -492,8 +511,9 @@ def main():
             except Exception as e:  # the oracle is a checker; the GPU numbers stand without it
                 out["cpu_baseline"] = {"value": None, "unit": "cycles/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(out))
-    lib.jagged_round_free(h_prep)
-    lib.machine_free(machine)
+    if h_prep is not None:
+        lib.jagged_round_free(h_prep)
+        lib.machine_free(machine)
     lib.close()
     if world > 1:
         dist.destroy_process_group()

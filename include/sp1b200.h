@@ -185,7 +185,8 @@ sp1b200_err sp1b200_machine_create(sp1b200_ctx* ctx, const uint32_t* h_blob, uin
 void sp1b200_machine_free(sp1b200_ctx* ctx, sp1b200_machine* machine);
 uint32_t sp1b200_machine_num_chips(const sp1b200_machine* machine);
 /* diagnostic: peak number of live registers of a chip's re-scheduled constraint program (selects the register-file tier of the
- * zerocheck kernels: <= 32 shared memory, <= 128 local memory, more is rejected by sp1b200_zerocheck); 0 if chip is out of range */
+ * zerocheck kernels: <= 32 shared memory, <= 128 local memory, <= 1024 global-memory workspace - the reference's largest tier,
+ * sys/lib/zerocheck/sequential.cu:298-335; more is rejected by sp1b200_zerocheck); 0 if chip is out of range */
 uint32_t sp1b200_machine_chip_regs(const sp1b200_machine* machine, uint32_t chip);
 
 /* ShardProver::zerocheck (crates/hypercube/src/prover/shard.rs:474-646): samples lambda, runs the max_log_row_count-round

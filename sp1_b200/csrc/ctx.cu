@@ -23,6 +23,8 @@ const char* sp1b200_set_error(const char* fmt, ...) {
     return g_err;
 }
 
+const char* sp1b200_last_error() { return g_err; }
+
 bool sp1b200_is_device_ptr(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }

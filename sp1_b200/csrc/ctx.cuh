@@ -70,6 +70,7 @@ __device__ __forceinline__ void sp1_mail_done(const Mail& m) {
 #endif
 
 const char* sp1b200_set_error(const char* fmt, ...);
+const char* sp1b200_last_error();   // the calling thread's most recent message
 
 // Every extern "C" entry point that takes a context runs with the context's device current and restores the caller's device on
 // exit: the CUDA current device is per host thread and defaults to 0, so a host runtime that drives several GPUs from one process

@@ -380,28 +380,44 @@ inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n
 
 inline Ext toExt(const E4& e) { return Ext{{e.c[0], e.c[1], e.c[2], e.c[3]}}; }
 
-const uint32_t* parse_vcol(const uint32_t* b, HostInteractions& H) {
+// every read is bounds-checked against the end of the blob and every column against the chip's widths: a blob exported for another
+// chip set must become an error, not an out-of-bounds read on host or device
+const uint32_t* parse_vcol(const uint32_t* b, const uint32_t* end, HostInteractions& H, uint32_t main_w, uint32_t prep_w) {
+    if (end - b < 2) return nullptr;
     VColDev v; v.n_terms = *b++; v.constant = *b++; v.term_start = (uint32_t)H.terms.size();
-    for (uint32_t i = 0; i < v.n_terms; i++) { H.terms.push_back(TermDev{b[0], b[1], b[2]}); b += 3; }
+    if ((uint64_t)v.n_terms * 3 > (uint64_t)(end - b)) return nullptr;
+    for (uint32_t i = 0; i < v.n_terms; i++) {
+        if ((b[0] != LEAF_MAIN && b[0] != LEAF_PREP) || b[1] >= (b[0] == LEAF_MAIN ? main_w : prep_w)) return nullptr;
+        H.terms.push_back(TermDev{b[0], b[1], b[2]}); b += 3;
+    }
     H.vcols.push_back(v);
     return b;
 }
 
 }  // namespace
 
-// parses the interaction section that follows the AIR records in the machine blob (called by sp1b200_machine_create)
-void* sp1b200_parse_interactions(const uint32_t* b, const uint32_t* end, size_t n_chips) {
+// parses the interaction section that follows the AIR records in the machine blob (called by sp1b200_machine_create);
+// widths[2k], widths[2k+1] = main / preprocessed width of chip k.  Returns nullptr (with the error set) on a malformed section.
+void* sp1b200_parse_interactions(const uint32_t* b, const uint32_t* end, size_t n_chips, const uint32_t* widths) {
     auto H = std::make_unique<HostInteractions>();
     H->per_chip.resize(n_chips);
     if (b >= end) return H.release();  // machine without interactions (zerocheck-only tests)
+    size_t k = 0;
     for (auto& chip : H->per_chip) {
+        const uint32_t mw = widths[2 * k], pw = widths[2 * k + 1];
+        if (end - b < 1) { sp1b200_set_error("machine_create: truncated interaction section (chip %zu)", k); return nullptr; }
         uint32_t n = *b++;
         for (uint32_t i = 0; i < n; i++) {
+            if (end - b < 3) { sp1b200_set_error("machine_create: truncated interaction section (chip %zu)", k); return nullptr; }
             InterDev in; in.is_send = *b++; in.arg_index = *b++; in.n_values = *b++; in.vcol_start = (uint32_t)H->vcols.size();
-            b = parse_vcol(b, *H);
-            for (uint32_t k = 0; k < in.n_values; k++) b = parse_vcol(b, *H);
+            if (in.n_values > 255) { sp1b200_set_error("machine_create: chip %zu interaction %u has %u values", k, i, in.n_values); return nullptr; }
+            for (uint32_t v = 0; v <= in.n_values; v++) {   // multiplicity, then the values
+                b = parse_vcol(b, end, *H, mw, pw);
+                if (!b) { sp1b200_set_error("machine_create: chip %zu interaction %u: malformed or out-of-range virtual column", k, i); return nullptr; }
+            }
             chip.push_back(in);
         }
+        k++;
     }
     return H.release();
 }

@@ -39,4 +39,4 @@ struct sp1b200_machine {
     void* interactions = nullptr;  // HostInteractions (gkr.cu)
 };
 
-void* sp1b200_parse_interactions(const uint32_t* b, const uint32_t* end, size_t n_chips);
+void* sp1b200_parse_interactions(const uint32_t* b, const uint32_t* end, size_t n_chips, const uint32_t* widths);

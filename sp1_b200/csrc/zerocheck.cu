@@ -27,8 +27,11 @@ using kb::Ext;
 using hf::E4;
 
 constexpr int ZC_BLOCK = 128;
-constexpr int ZC_LOCAL_REGS = 128;
-constexpr size_t ZC_MAX_PIECES = 16;  // fallback tier: register file in local memory
+constexpr int ZC_LOCAL_REGS = 128;    // second tier: register file in local memory
+constexpr int ZC_GLOBAL_REGS = 1024;  // last tier: register file in a global-memory workspace (the reference's largest tier,
+                                      // sys/lib/zerocheck/sequential.cu:298-335, keeps K regs[1024] in per-thread local memory)
+constexpr unsigned ZC_GLOBAL_MAXB = 148 * 2;  // blocks of a global-tier job: bounds the workspace (blocks x regs x 3 nodes x 128 x 16 B)
+constexpr size_t ZC_MAX_PIECES = 16;
 
 template <class K> struct Ops;
 template <> struct Ops<uint32_t> {
@@ -73,19 +76,29 @@ __device__ __forceinline__ int find_job(const J* __restrict__ jobs, int n, uint3
 
 // register file: every register holds the value at ALL THREE evaluation nodes (the program is decoded once per row pair and
 // the three evaluations run in lockstep: one instruction fetch, three independent products in flight, one pass over the
-// columns).  Shared memory [reg][node][thread] (SMEM), or a local array for programs whose pressure does not fit.
-template <class K, bool SMEM> struct RegFile;
-template <class K> struct RegFile<K, true> {
+// columns).  RF_SMEM: shared memory [reg][node][thread]; RF_LOCAL: a local array (<= 128 registers); RF_GLOBAL: the same
+// [reg][node][thread] layout in a per-block slice of a global workspace (coalesced, sized by the program's real pressure, L1/L2
+// resident for the hot registers) for programs of up to 1024 live registers.
+enum { RF_SMEM = 0, RF_LOCAL = 1, RF_GLOBAL = 2 };
+template <class K, int RF> struct RegFile;
+template <class K> struct RegFile<K, RF_SMEM> {
     K* base;
-    __device__ __forceinline__ RegFile(unsigned char* smem) : base(reinterpret_cast<K*>(smem) + threadIdx.x) {}
+    __device__ __forceinline__ RegFile(unsigned char* smem, void*, uint32_t) : base(reinterpret_cast<K*>(smem) + threadIdx.x) {}
     __device__ __forceinline__ K get(uint32_t r, int n) const { return base[(r * 3 + n) * ZC_BLOCK]; }
     __device__ __forceinline__ void set(uint32_t r, int n, const K& v) { base[(r * 3 + n) * ZC_BLOCK] = v; }
 };
-template <class K> struct RegFile<K, false> {
+template <class K> struct RegFile<K, RF_LOCAL> {
     K regs[ZC_LOCAL_REGS * 3];
-    __device__ __forceinline__ RegFile(unsigned char*) {}
+    __device__ __forceinline__ RegFile(unsigned char*, void*, uint32_t) {}
     __device__ __forceinline__ K get(uint32_t r, int n) const { return regs[r * 3 + n]; }
     __device__ __forceinline__ void set(uint32_t r, int n, const K& v) { regs[r * 3 + n] = v; }
+};
+template <class K> struct RegFile<K, RF_GLOBAL> {
+    K* base;
+    __device__ __forceinline__ RegFile(unsigned char*, void* ws, uint32_t ws_regs)
+        : base(static_cast<K*>(ws) + (size_t)blockIdx.x * ws_regs * 3 * ZC_BLOCK + threadIdx.x) {}
+    __device__ __forceinline__ K get(uint32_t r, int n) const { return base[(size_t)(r * 3 + n) * ZC_BLOCK]; }
+    __device__ __forceinline__ void set(uint32_t r, int n, const K& v) { base[(size_t)(r * 3 + n) * ZC_BLOCK] = v; }
 };
 
 // column values at the nodes t = 0, 2, 4 of row pair i:  z, z + 2d, z + 4d  with d = o - z (o = 0 past the last real row)
@@ -105,10 +118,11 @@ __device__ __forceinline__ void load_nodes(const K* __restrict__ base, uint32_t 
 // partial[(blockIdx.x * 3 + node) * 3 + {0,1,2}] =
 //   0: sum_rows E[i] * [constraints](node)     1 (node 0 only): sum_rows E[i] * sum_j g_j col_j(0)     2 (node 0 only): same at 1
 // FIRST (round 0): the constraints vanish on the boolean rows, so node 0 is skipped (N0 = 1).
-template <class K, bool SMEM, bool FIRST>
+template <class K, int RF, bool FIRST>
 __global__ void __launch_bounds__(ZC_BLOCK) zc_sum_kernel(const ZcJob* __restrict__ jobs, int n_jobs, const ChipProg* __restrict__ chips,
                                                           const uint32_t* __restrict__ pv, const uint32_t* __restrict__ gkr_pows,
-                                                          const uint32_t* __restrict__ E, uint32_t* __restrict__ partial) {
+                                                          const uint32_t* __restrict__ E, uint32_t* __restrict__ partial,
+                                                          void* __restrict__ ws, uint32_t ws_regs) {
     using O = Ops<K>;
     constexpr int N0 = FIRST ? 1 : 0;
     extern __shared__ __align__(16) unsigned char zc_smem[];
@@ -119,7 +133,7 @@ __global__ void __launch_bounds__(ZC_BLOCK) zc_sum_kernel(const ZcJob* __restric
     const K* prep = static_cast<const K*>(job.prep);
     const uint64_t h = job.h;
     const uint64_t terms = (h + 1) / 2;
-    RegFile<K, SMEM> rf(zc_smem);
+    RegFile<K, RF> rf(zc_smem, ws, ws_regs);
     Ext acc[5];  // constraints at nodes 0,1,2 ; opening-batching term at 0 and at 1
 #pragma unroll
     for (int a = 0; a < 5; a++) acc[a] = kb::ext_zero();
@@ -386,7 +400,13 @@ sp1b200_err sp1b200_machine_create(sp1b200_ctx* ctx, const uint32_t* h_blob, uin
         }
         m->chips.push_back(p); m->host.push_back(std::move(hp));
     }
-    m->interactions = sp1b200_parse_interactions(b, end, n);
+    {
+        std::vector<uint32_t> widths;
+        for (auto& c : m->chips) { widths.push_back(c.main_w); widths.push_back(c.prep_w); }
+        widths.push_back(0);
+        m->interactions = sp1b200_parse_interactions(b, end, n, widths.data());
+        if (!m->interactions) return sp1b200_last_error();   // message set by the parser
+    }
     // re-schedule every chip's program for the shared-memory register file (zc_lower.hpp) and upload the streams
     std::vector<ZcInstr> all;
     std::vector<size_t> zc_off(n);
@@ -478,7 +498,7 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
         St& s = S[k];
         s.h = h_heights[k];
         if (s.h > ((uint64_t)1 << mlr)) return sp1b200_set_error("zerocheck: chip %zu height exceeds 2^%u", k, mlr);
-        if (p.zc_regs > ZC_LOCAL_REGS) return sp1b200_set_error("zerocheck: chip %zu needs %u live registers (> %d)", k, p.zc_regs, ZC_LOCAL_REGS);
+        if (p.zc_regs > ZC_GLOBAL_REGS) return sp1b200_set_error("zerocheck: chip %zu needs %u live registers (> %d)", k, p.zc_regs, ZC_GLOBAL_REGS);
         s.zeta = gp;
         std::vector<E4> rev(pw.begin(), pw.begin() + p.n_constraints);
         std::reverse(rev.begin(), rev.end());
@@ -511,7 +531,8 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     // ---- the whole launch plan is known up front (heights halve deterministically): job tables of every round, one upload ----
     // tiers of the shared-memory register file (registers per thread); chips above the last tier use the local-memory kernel
     static const uint32_t TIER_REGS[3] = {8, 16, 32};  // x 3 nodes x 16 B x 128 threads = 48 / 96 / 192 KiB per block (EF rounds)
-    auto tier_of = [&](uint32_t regs) { for (int t = 0; t < 3; t++) if (regs <= TIER_REGS[t]) return t; return 3; };
+    auto tier_of = [&](uint32_t regs) { for (int t = 0; t < 3; t++) if (regs <= TIER_REGS[t]) return t; return regs <= (uint32_t)ZC_LOCAL_REGS ? 3 : 4; };
+    size_t ws_bytes = 0;  // global register-file workspace: worst launch of the last tier (EF rounds: 16 B per register and node)
     struct Launch { size_t job0; uint32_t n_jobs, blocks, regs; int tier; };
     struct RoundPlan { std::vector<Launch> sums; size_t fix0; uint32_t fix_jobs, fix_blocks; std::vector<uint32_t> chip_of_job; size_t job0; };
     std::vector<RoundPlan> plan(mlr);
@@ -536,13 +557,14 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
                 return static_cast<const uint32_t*>(in_main(k)) + (uint64_t)p.main_w * hcur[k] * 4;
             };
             uint32_t blocks_round = 0;
-            for (int tier = 0; tier < 4; tier++) {
+            for (int tier = 0; tier < 5; tier++) {
                 Launch Lc{jobs.size(), 0, 0, 0, tier};
                 for (size_t k = 0; k < nchips; k++) {
                     const ChipProg& p = m->chips[k];
                     if (!hcur[k] || tier_of(p.zc_regs) != tier) continue;
                     unsigned nb = blocks_for((hcur[k] + 1) / 2, ZC_BLOCK);
                     if (nb > MAXB) nb = MAXB;
+                    if (tier == 4 && nb > ZC_GLOBAL_MAXB) nb = ZC_GLOBAL_MAXB;
                     // short rounds: a thread would interpret the whole program for its row pair (hundreds of microseconds for the
                     // wide chips); the self-contained pieces run side by side instead, one job each
                     const auto& pieces = m->host[k].zc_pieces;
@@ -562,7 +584,10 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
                     }
                     Lc.regs = std::max(Lc.regs, p.zc_regs);
                 }
-                if (Lc.n_jobs) { R.sums.push_back(Lc); blocks_round += Lc.blocks; }
+                if (Lc.n_jobs) {
+                    R.sums.push_back(Lc); blocks_round += Lc.blocks;
+                    if (tier == 4) ws_bytes = std::max(ws_bytes, (size_t)Lc.blocks * Lc.regs * 3 * ZC_BLOCK * 16);
+                }
             }
             max_blocks = std::max(max_blocks, blocks_round);
             max_jobs = std::max<uint32_t>(max_jobs, (uint32_t)R.chip_of_job.size());
@@ -588,16 +613,20 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     if ((size_t)max_jobs * 36 > SP1_MAIL_WORDS) return sp1b200_set_error("zerocheck: %u chips exceed the mailbox payload", max_jobs);
     d_sums = sp1b200_mail_dev(ctx);
     SP1_CUDA(cudaMemsetAsync(d_final, 0, (wsum ? wsum : 1) * 16, st));
+    void* d_ws = nullptr;
+    if (ws_bytes) SP1_TRY(mem.alloc(&d_ws, ws_bytes));
     auto launch_sum = [&](const Launch& Lc, bool ext, uint32_t* part) -> sp1b200_err {
         auto go = [&](auto kern, size_t smem) -> sp1b200_err {
             // the static reduction buffer counts against the 48 KiB default as well: opt in early
             if (smem > 32 * 1024) SP1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SP1_LAUNCH(ctx, kern, Lc.blocks, ZC_BLOCK, smem, d_jobs + Lc.job0, (int)Lc.n_jobs, m->d_chips, d_pv, d_gw, d_E[ecur], part);
+            SP1_LAUNCH(ctx, kern, Lc.blocks, ZC_BLOCK, smem, d_jobs + Lc.job0, (int)Lc.n_jobs, m->d_chips, d_pv, d_gw, d_E[ecur], part, d_ws,
+                       Lc.regs);
             return nullptr;
         };
-        if (Lc.tier == 3) return ext ? go(zc_sum_kernel<Ext, false, false>, 0) : go(zc_sum_kernel<uint32_t, false, true>, 0);
+        if (Lc.tier == 4) return ext ? go(zc_sum_kernel<Ext, RF_GLOBAL, false>, 0) : go(zc_sum_kernel<uint32_t, RF_GLOBAL, true>, 0);
+        if (Lc.tier == 3) return ext ? go(zc_sum_kernel<Ext, RF_LOCAL, false>, 0) : go(zc_sum_kernel<uint32_t, RF_LOCAL, true>, 0);
         const size_t regs = Lc.regs;  // the file is sized by the launch's worst chip: regs x 3 nodes x block
-        return ext ? go(zc_sum_kernel<Ext, true, false>, regs * 3 * ZC_BLOCK * 16) : go(zc_sum_kernel<uint32_t, true, true>, regs * 3 * ZC_BLOCK * 4);
+        return ext ? go(zc_sum_kernel<Ext, RF_SMEM, false>, regs * 3 * ZC_BLOCK * 16) : go(zc_sum_kernel<uint32_t, RF_SMEM, true>, regs * 3 * ZC_BLOCK * 4);
     };
 
     t_setup.reset();

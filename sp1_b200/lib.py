@@ -211,6 +211,10 @@ class Lib:
         self._chk(self.L.sp1b200_machine_create(self.ctx, _ptr(blob), C.c_uint64(blob.size), C.byref(h)))
         return h
 
+    def machine_chip_regs(self, h, chip):
+        """peak live registers of a chip's re-scheduled constraint program (register-file tier of the zerocheck kernels)"""
+        return int(self.L.sp1b200_machine_chip_regs(h, C.c_uint32(chip)))
+
     def machine_free(self, h):
         self.L.sp1b200_machine_free(self.ctx, h)
 

@@ -68,13 +68,16 @@ class Asm:
         return w
 
 
-def synth_chip(groups, with_prep, kconst=7, deep=False):
+def synth_chip(groups, with_prep, kconst=7, deep=False, n_constraints=None, extra_cols=0):
     """-> (machine words for this chip, main_w, prep_w).
+    n_constraints (calibrated chips): further constraints of degree 2-3 are added round-robin over the groups until the chip has
+    that many (at most 9 per group); each is implied by the template's relations, so the same traces satisfy them and they vanish on
+    the all-zero padding row.  extra_cols: unconstrained filler columns after the template (exact reference widths, e.g. 682).
     deep=True emits the SAME constraints in an order with long-lived intermediates (all products a_g b_g first, consumed in
     reverse order afterwards): the register pressure of the program grows with `groups`, which exercises the larger
     register-file tiers of the zerocheck kernels (the flat order needs a handful of registers whatever the chip size)."""
     a = Asm()
-    main_w = 6 * groups + (1 if with_prep else 0)
+    main_w = 6 * groups + (1 if with_prep else 0) + extra_cols
     prep_w = 1 if with_prep else 0
     pv0 = a.public(0)
     kc = a.const(kconst)
@@ -106,10 +109,29 @@ def synth_chip(groups, with_prep, kconst=7, deep=False):
         H = a.leaf(LEAF_MAIN, 6 * groups)
         A0 = a.leaf(LEAF_MAIN, 0)
         a.assert_zero(a.op(ADD, a.op(NEG, a.op(MUL, G, A0)), H))  # -(g a) + h
+    if n_constraints is not None:
+        have = len(a.asserts)
+        kind, g = 0, 0
+        while have < n_constraints and kind < 5:
+            A, B, Cc, D, E, Fc = (a.leaf(LEAF_MAIN, 6 * g + i) for i in range(6))
+            if kind == 0:
+                a.assert_zero(a.op(MUL, D, a.op(SUB, Cc, a.op(MUL, A, B))))     # d (c - a b)          degree 3
+            elif kind == 1:
+                a.assert_zero(a.op(SUB, E, a.op(MUL, Cc, D)))                   # e - c d
+            elif kind == 2:
+                a.assert_zero(a.op(MUL, D, a.op(SUB, E, Cc)))                   # d (e - c)            (d boolean, e = c d)
+            elif kind == 3:
+                a.assert_zero(a.op(MUL, B, a.op(SUB, Fc, a.op(ADD, A, kpv))))   # b (f - a - K pv0)
+            else:
+                a.assert_zero(a.op(MUL, E, a.op(SUB, D, one)))                  # e (d - 1)
+            have += 1
+            g += 1
+            if g == groups:
+                g, kind = 0, kind + 1
     return a.words(main_w, prep_w), main_w, prep_w
 
 
-def synth_trace(rng, height, groups, with_prep, pv0_canonical, kconst=7):
+def synth_trace(rng, height, groups, with_prep, pv0_canonical, kconst=7, extra_cols=0):
     """canonical-domain generation, returned as Montgomery words, column-major [w, height]"""
     cols = []
     prep = None
@@ -128,6 +150,8 @@ def synth_trace(rng, height, groups, with_prep, pv0_canonical, kconst=7):
         gcol = rng.integers(0, P, height, dtype=np.uint64)
         cols.append(gcol * a0 % P)
         prep = to_monty(np.stack([gcol]))
+    for _ in range(extra_cols):
+        cols.append(rng.integers(0, P, height, dtype=np.uint64))
     main = to_monty(np.stack(cols)) if height else np.zeros((len(cols), 0), np.uint32)
     if with_prep and not height:
         prep = np.zeros((1, 0), np.uint32)
@@ -182,6 +206,41 @@ def synth_interactions(groups, with_prep, inter_groups=None):
     return w
 
 
+def synth_interactions_calibrated(groups, with_prep, values_per_send):
+    """Interactions with the message statistics of a real chip (sp1_b200/chip_stats.json): one send + one receive of the same
+    tuple and multiplicity per entry of `values_per_send` (value counts, e.g. 4 = byte lookup, 5 = CPU state, 9 = memory access),
+    so the cumulative LogUp sum is zero.  Values are linear combinations of the group columns."""
+    kinds = [5, 7, 3, 2, 6, 9]   # InteractionKind indices: Byte, State, Memory, Program, Syscall, Global (any stable labels)
+    sends, recvs = [], []
+    for i, nv in enumerate(values_per_send):
+        g = i % groups
+        a, b, c, d, e, f = (6 * g + j for j in range(6))
+        menu = [
+            [(LEAF_MAIN, a, 1)], [(LEAF_MAIN, b, 1), (LEAF_MAIN, a, 2)], ([(LEAF_MAIN, c, 1)], 5), [(LEAF_MAIN, e, 3)], [(LEAF_MAIN, f, 1)],
+            [(LEAF_MAIN, a, 1), (LEAF_MAIN, b, 1), (LEAF_MAIN, c, 1)], ([(LEAF_MAIN, d, 1)], 1), [(LEAF_MAIN, f, 2), (LEAF_MAIN, e, 1)],
+            [(LEAF_MAIN, b, 7)], [(LEAF_MAIN, c, 1), (LEAF_MAIN, d, 4)], [(LEAF_MAIN, a, 3), (LEAF_MAIN, f, 1)], [(LEAF_MAIN, e, 1), (LEAF_MAIN, b, 2)],
+        ]
+        vals = []
+        for k in range(nv):
+            m = menu[(k + i) % len(menu)]
+            vals.append(_vcol(*m) if isinstance(m, tuple) else _vcol(m))
+        mult = _vcol([(LEAF_MAIN, d, 1)]) if i % 3 else _vcol([], constant=1)   # boolean column or the constant 1
+        kind = kinds[i % len(kinds)]
+        sends.append((1, kind, mult, vals))
+        recvs.append((0, kind, mult, vals))
+    inter = sends + recvs
+    if with_prep:
+        gv = [_vcol([(LEAF_PREP, 0, 1)]), _vcol([(LEAF_MAIN, 6 * groups, 1)])]
+        inter.insert(len(sends), (1, 2, _vcol([(LEAF_MAIN, 3, 1)]), gv))
+        inter.append((0, 2, _vcol([(LEAF_MAIN, 3, 1)]), gv))
+    w = [len(inter)]
+    for is_send, kind, mult, vals in inter:
+        w += [is_send, kind, len(vals)] + mult
+        for v in vals:
+            w += v
+    return w
+
+
 def machine_blob_with_interactions(chip_words, inter_words):
     w = [len(chip_words)]
     for cw in chip_words:
@@ -191,13 +250,13 @@ def machine_blob_with_interactions(chip_words, inter_words):
     return np.array(w, dtype=np.uint32)
 
 
-def synth_trace_cuda(height, groups, with_prep, pv0_canonical, seed, device, kconst=7):
+def synth_trace_cuda(height, groups, with_prep, pv0_canonical, seed, device, kconst=7, extra_cols=0):
     """same trace family generated on the GPU with torch (bench input only): -> (main [w*height] int32 Montgomery words
     column-major, prep [height] or None)"""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    w = 6 * groups + (1 if with_prep else 0)
+    w = 6 * groups + (1 if with_prep else 0) + extra_cols
     if height == 0:
         return torch.zeros(0, dtype=torch.int32, device=device), (torch.zeros(0, dtype=torch.int32, device=device) if with_prep else None)
     out = torch.empty((w, height), dtype=torch.int32, device=device)
@@ -221,4 +280,6 @@ def synth_trace_cuda(height, groups, with_prep, pv0_canonical, seed, device, kco
         gc = torch.randint(0, P, (height,), dtype=torch.int64, device=device, generator=g)
         out[6 * groups] = mont(gc * a0 % P)
         prep = mont(gc)
+    for j in range(extra_cols):
+        out[6 * groups + (1 if with_prep else 0) + j] = mont(torch.randint(0, P, (height,), dtype=torch.int64, device=device, generator=g))
     return out.reshape(-1), prep

@@ -28,12 +28,25 @@ WORKLOADS = {
     "S2": (190_000_000, "sha-bench-like shard, 2^22 cycles, ~1.9e8 cells, C=91"),
     "S3": (402_653_184, "full shard (ELEMENT_THRESHOLD = 2^28 + 2^27 cells), C=192"),
     "tiny": (1 << 21, "smoke-sized shard"),
+    # calibrated variants (suffix c): every chip carries the constraint count and the LogUp interaction count / message lengths that
+    # tools/chip_stats.py reads off the reference's Rust eval functions (sp1_b200/chip_stats.json) instead of the light template
+    "S1c": (1 << 25, "S1 with calibrated chips (constraints + interactions per chip from chip_stats.json)"),
+    "S2c": (190_000_000, "S2 with calibrated chips (constraints + interactions per chip from chip_stats.json)"),
+    # precompile-heavy shards (BASELINE config 3): 30 % of the area in one 682-column precompile table
+    "S3p": (402_653_184, "full shard, 30 % of the area in a 682-column precompile table (keccak-permute-like), light chips"),
+    "S3c": (402_653_184, "full shard, 30 % of the area in a 682-column precompile table, calibrated chips"),
+    "tinyc": (1 << 21, "smoke-sized shard, calibrated chips + a small precompile table"),
 }
+PRECOMPILE = ("KeccakPermute", 682)       # 682-wide precompile columns
+PRECOMPILE_SHARE = {"S3p": 0.30, "S3c": 0.30, "tinyc": 0.30}
+CALIBRATED = {"S1c", "S2c", "S3c", "tinyc"}
+BASE_OF = {"S1c": "S1", "S2c": "S2", "S3p": "S3", "S3c": "S3", "tinyc": "tiny"}
 
 
 def shard_shapes(workload, seed=42, max_log_rows=22):
-    """-> (prep [(rows, cols)], main [(rows, cols)]) in BTreeMap (name) order, as the reference commits them."""
-    area = WORKLOADS[workload][0]
+    """-> (prep [(rows, cols)], main [(rows, cols)]) in BTreeMap (name) order, as the reference commits them (core chips only; the
+    precompile table of the S3p / S3c workloads is added by synthetic_machine)."""
+    area = int(WORKLOADS[workload][0] * (1.0 - PRECOMPILE_SHARE.get(workload, 0.0)))
     rng = np.random.default_rng(seed)
     chips = sorted(CORE_CHIPS)
     weights = rng.dirichlet(np.ones(len(chips)) * 2.0)
@@ -78,30 +91,62 @@ def random_dense_cuda(shapes, seed, device):
     return torch.randint(0, P, (area_of(shapes),), dtype=torch.int32, device=device, generator=g)
 
 
+_STATS = None
+
+
+def chip_stats():
+    """sp1_b200/chip_stats.json (tools/chip_stats.py): per chip {constraints, interactions, values_per_interaction}"""
+    global _STATS
+    if _STATS is None:
+        import json
+        import os
+        _STATS = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "chip_stats.json")))["chips"]
+    return _STATS
+
+
 # ---- full-shard synthetic machine (constraints + interactions) for bench.py and the scale tests -------------------------------
 def synthetic_machine(workload, seed=42, max_log_rows=22, scale=1.0):
-    """-> dict(names, specs [(height, groups, with_prep)], blob, main_shapes [(rows, cols)], prep_shapes)
-    chips = the core cluster's chips (CORE_CHIPS widths -> 6-column constraint groups) + the three preprocessed tables,
-    in name order; heights from shard_shapes (multiples of 32), optionally scaled down by `scale` (CPU baseline sample)."""
+    """-> dict(names, specs [(height, groups, with_prep[, extra_cols])], blob, main_shapes [(rows, cols)], prep_shapes)
+    chips = the core cluster's chips (CORE_CHIPS widths -> 6-column constraint groups) + the three preprocessed tables (+ the
+    precompile table of the S3p / S3c workloads), in name order; heights from shard_shapes (multiples of 32), optionally scaled
+    down by `scale` (CPU baseline sample).  Calibrated workloads take each chip's constraint count and interaction message
+    lengths from chip_stats.json."""
     from . import synth_air as SA
     prep, main = shard_shapes(workload, seed=seed, max_log_rows=max_log_rows)
+    calibrated = workload in CALIBRATED
+    stats = chip_stats() if calibrated else {}
     chips = sorted(CORE_CHIPS)
-    entries = []
+    entries = []   # (name, groups, with_prep, rows, extra_cols)
     for (name, w), (rows, _) in zip(chips, main):
-        entries.append((name, max(1, round(w / 6)), False, rows))
+        entries.append((name, max(1, round(w / 6)), False, rows, 0))
     for (name, w, _), (rows, _) in zip(sorted(PREP_CHIPS), prep):
-        entries.append((name, max(1, round(w / 6)), True, rows))
+        entries.append((name, max(1, round(w / 6)), True, rows, 0))
+    share = PRECOMPILE_SHARE.get(workload, 0.0)
+    if share:
+        pname, pw = PRECOMPILE
+        rows = int(WORKLOADS[workload][0] * share / pw) // 32 * 32
+        entries.append((pname, pw // 6, False, min(rows, 1 << max_log_rows), pw - 6 * (pw // 6)))
     entries.sort(key=lambda e: e[0])
     names, specs, words, iwords = [], [], [], []
-    for name, g, wp, rows in entries:
+    for name, g, wp, rows, extra in entries:
         h = int(rows * scale) // 32 * 32 if rows else 0
         if rows and not h:
             h = 32
-        names.append(name); specs.append((h, g, wp))
-        cw, _, _ = SA.synth_chip(g, wp)
+        names.append(name); specs.append((h, g, wp, extra))
+        st = stats.get(name) if calibrated else None
+        if name == PRECOMPILE[0] and calibrated:
+            # a permutation precompile: ~2 constraints per column, a handful of wide memory / syscall interactions
+            st = {"constraints": 2 * PRECOMPILE[1], "values_per_interaction": [9] * 50 + [5] * 4}
+        if st and "constraints" in st:
+            cw, _, _ = SA.synth_chip(g, wp, n_constraints=min(max(st["constraints"], 4 * g), 9 * g), extra_cols=extra)
+            v = st["values_per_interaction"]
+            iw = SA.synth_interactions_calibrated(g, wp, [max(1, min(x, 12)) for x in v[::2]] or [4])   # half are sends, half receives
+        else:
+            cw, _, _ = SA.synth_chip(g, wp, extra_cols=extra)
+            iw = SA.synth_interactions(g, wp, inter_groups=-(-g // 3))
         words.append(cw)
-        iwords.append(SA.synth_interactions(g, wp, inter_groups=-(-g // 3)))
+        iwords.append(iw)
     blob = SA.machine_blob_with_interactions(words, iwords)
-    main_shapes = [(h, 6 * g + (1 if wp else 0)) for h, g, wp in specs]
-    prep_shapes = [(h, 1) for h, g, wp in specs if wp]
+    main_shapes = [(h, 6 * g + (1 if wp else 0) + extra) for h, g, wp, extra in specs]
+    prep_shapes = [(h, 1) for h, g, wp, extra in specs if wp]
     return dict(names=names, specs=specs, blob=blob, main_shapes=main_shapes, prep_shapes=prep_shapes)

@@ -58,10 +58,10 @@ def fullsize_inputs(workload, seed):
     mach = W.synthetic_machine(workload, seed=42)
     rng = np.random.default_rng(seed)
     mains, preps = [], []
-    for h, g, wp in mach["specs"]:
-        m_, p_ = SA.synth_trace(rng, h, g, wp, FULL_PV0)
+    for h, g, wp, extra in mach["specs"]:
+        m_, p_ = SA.synth_trace(rng, h, g, wp, FULL_PV0, extra_cols=extra)
         mains.append(m_); preps.append(p_)
     pv = O.to_monty(np.array([FULL_PV0, 5, 6, 7]))
     ch = O.Challenger()
     ch.observe(O.rand_field(rng, 9))
-    return mach, [h for h, _, _ in mach["specs"]], mains, preps, pv, ch
+    return mach, [s_[0] for s_ in mach["specs"]], mains, preps, pv, ch

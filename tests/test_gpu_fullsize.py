@@ -10,7 +10,7 @@ from tests import oracle_lib as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("workload", ["S1", "S2", "S3"])
+@pytest.mark.parametrize("workload", ["S1", "S2", "S3", "S2c", "S3c"])
 def test_full_size_gpu_proof_is_accepted_by_the_restated_reference_verifier(workload):
     import torch
     from sp1_b200 import Lib
@@ -21,12 +21,12 @@ def test_full_size_gpu_proof_is_accepted_by_the_restated_reference_verifier(work
     dev = torch.device("cuda", 0)
     mach = W.synthetic_machine(workload, seed=42)
     specs, names = mach["specs"], mach["names"]
-    heights = [h for h, _, _ in specs]
+    heights = [s_[0] for s_ in specs]
     pv0 = 12345
     pv = O.to_monty(np.array([pv0, 5, 6, 7]))
     mains, preps = [], []
-    for i, (h, g, wp) in enumerate(specs):
-        m_, p_ = SA.synth_trace_cuda(h, g, wp, pv0, 7000 + i, dev)
+    for i, (h, g, wp, extra) in enumerate(specs):
+        m_, p_ = SA.synth_trace_cuda(h, g, wp, pv0, 7000 + i, dev, extra_cols=extra)
         mains.append(m_)
         if wp:
             preps.append(p_)
@@ -35,7 +35,7 @@ def test_full_size_gpu_proof_is_accepted_by_the_restated_reference_verifier(work
     del mains, preps
     lib = Lib(device=0)                                   # core parameters (sp1b200_default_core_params)
     machine = lib.machine_create(mach["blob"])
-    prep_rows = [h for h, _, wp in specs if wp]
+    prep_rows = [s_[0] for s_ in specs if s_[2]]
     pc, h_prep = lib.jagged_commit_dense(d_prep, prep_rows, [1] * len(prep_rows))
     st0 = HostChallenger().st.copy()
     st = st0.copy()

@@ -28,6 +28,10 @@ def _ext_add(a, b):
     # long-lived intermediates: register pressure ~ groups -> every register-file tier (<= 8, <= 16, <= 32 in shared memory,
     # local-memory fallback above) in one proof, next to a flat chip
     ([(512, 6, False, True), (300, 14, True, True), (1024, 28, False, True), (96, 40, False, True), (2048, 3, True)], 12),
+    # the reference's largest register tiers (sys/lib/zerocheck/sequential.cu:298-335: 256 / 512 / 1024 registers): programs whose
+    # re-scheduled live set is ~250, ~500 and ~1000 registers -> the global-memory register file, next to a shared-memory chip;
+    # heights on both sides of the "pieces" threshold (<= 16 blocks of 128 row pairs)
+    ([(192, 250, False, True), (64, 500, True, True), (8192, 3, True), (96, 1000, False, True), (6000, 300, False, True)], 13),
 ])
 def test_zerocheck_matches_oracle(spec, mlr):
     import torch
@@ -42,6 +46,9 @@ def test_zerocheck_matches_oracle(spec, mlr):
 
     lib = Lib(0, max_log_row_count=mlr, log_stacking_height=min(mlr, 21))
     mach = lib.machine_create(blob)
+    if any(len(s_) > 3 and s_[1] >= 250 for s_ in spec):
+        regs = [lib.machine_chip_regs(mach, k) for k in range(len(spec))]
+        assert max(regs) > 900 and sorted(regs)[-2] > 450 and min(regs) <= 32, regs   # the tiers the case is meant to exercise
     hc = HostChallenger(ch.st.copy())
     alpha = hc.sample(4); gamma = hc.sample(4)
     # claims = sum_j gamma^(j+1) * opening_j, chip by chip (main then prep), from the openings at the gkr point

@@ -26,26 +26,45 @@ def test_synthetic_machine_is_consistent():
     m = W.synthetic_machine("tiny", seed=42)
     assert m["names"] == sorted(m["names"])
     assert len(m["names"]) == len(m["specs"]) == len(m["main_shapes"])
-    for (h, g, wp), (rows, cols) in zip(m["specs"], m["main_shapes"]):
-        assert rows == h and cols == 6 * g + (1 if wp else 0)
+    for (h, g, wp, extra), (rows, cols) in zip(m["specs"], m["main_shapes"]):
+        assert rows == h and cols == 6 * g + (1 if wp else 0) + extra
     assert int(m["blob"][0]) == len(m["specs"])
     small = W.synthetic_machine("S2", seed=42, scale=1 / 64)
     assert W.area_of(small["main_shapes"]) < W.area_of(W.synthetic_machine("S2", seed=42)["main_shapes"]) / 32
 
 
-def test_synthetic_traces_satisfy_constraints_and_interactions():
-    """a scaled-down copy of the bench machine: the oracle proves it and its restated verifier accepts (constraints hold on every
-    real row, the LogUp cumulative sum is zero)"""
-    m = W.synthetic_machine("tiny", seed=42, scale=1 / 256)
+@pytest.mark.parametrize("workload", ["tiny", "tinyc"])
+def test_synthetic_traces_satisfy_constraints_and_interactions(workload):
+    """a scaled-down copy of the bench machine (light and calibrated + precompile table): the oracle proves it and its restated
+    verifier accepts (constraints hold on every real row, the LogUp cumulative sum is zero)"""
+    m = W.synthetic_machine(workload, seed=42, scale=1 / 256)
     rng = np.random.default_rng(3)
     mains, preps = [], []
-    for h, g, wp in m["specs"]:
-        a, p = SA.synth_trace(rng, h, g, wp, 12345)
+    for h, g, wp, extra in m["specs"]:
+        a, p = SA.synth_trace(rng, h, g, wp, 12345, extra_cols=extra)
         mains.append(a); preps.append(p)
     pv = O.to_monty(np.array([12345, 5, 6, 7]))
-    heights = [h for h, _, _ in m["specs"]]
+    heights = [s_[0] for s_ in m["specs"]]
     mlr = max(5, int(np.ceil(np.log2(max(heights + [2])))))
     ch = O.Challenger()
     pc, words = O.prove_shard_verify(m["blob"], heights, mains, preps, m["names"], pv, min(mlr, 6), mlr, ch, num_queries=4, pow_bits=2,
                                      batch_pow_bits=1, gkr_pow_bits=2)
     assert words[0] == 5 and words.size > 100
+
+
+def test_calibrated_machine_follows_the_chip_statistics():
+    """calibrated workloads: every core chip carries the constraint count (clamped to 4..9 per 6-column group) and the number /
+    lengths of LogUp messages that tools/chip_stats.py read off the reference's Rust eval functions; the precompile-heavy shard
+    puts ~30 % of its area into one 682-column table"""
+    st = W.chip_stats()
+    assert len(st) >= 30 and all("source" in v or "error" in v for v in st.values())
+    light, cal = W.synthetic_machine("S2", seed=42), W.synthetic_machine("S2c", seed=42)
+    assert light["main_shapes"] == cal["main_shapes"] and light["names"] == cal["names"]
+    assert cal["blob"].size > 2 * light["blob"].size          # more constraints and far more interaction words
+    m = W.synthetic_machine("S3c", seed=42)
+    k = m["names"].index(W.PRECOMPILE[0])
+    rows, cols = m["main_shapes"][k]
+    assert cols == 682
+    share = rows * cols / W.area_of(m["main_shapes"])
+    assert 0.27 < share < 0.33
+    assert abs(W.area_of(m["main_shapes"]) / W.WORKLOADS["S3c"][0] - 1) < 0.02

@@ -110,10 +110,11 @@ class OracleShard:
         self.O, self.L = O, O.lib()
         self.cores = _oracle_threads(self.L)
         self.mach = W.synthetic_machine(workload_name, seed=42, scale=scale)
+        self.params = W.params_of(workload_name)
         rng = np.random.default_rng(7)
         self.mains, self.preps = [], []
-        for h, g, wp, extra in self.mach["specs"]:
-            m_, p_ = SA.synth_trace(rng, h, g, wp, 12345, extra_cols=extra)
+        for sp in self.mach["specs"]:
+            m_, p_ = SA.synth_trace(rng, sp.h, sp.g, sp.wp, 12345, extra_cols=sp.extra, extra_prep=sp.extra_prep)
             self.mains.append(m_); self.preps.append(p_)
         self.pv = O.to_monty(np.array([12345, 5, 6, 7]))
         self.cells = W.area_of(self.mach["main_shapes"])
@@ -125,7 +126,7 @@ class OracleShard:
         self.L.orc_set_skip_verify(1)
         t0 = time.time()
         self.O.prove_shard_verify(self.mach["blob"], [s_[0] for s_ in self.mach["specs"]], self.mains, self.preps, self.mach["names"],
-                                  self.pv, 21, 22, ch)
+                                  self.pv, self.params["log_stacking_height"], self.params["max_log_row_count"], ch)
         wall = time.time() - t0
         self.L.orc_set_skip_verify(0)
         t = (ctypes.c_double * 5)()
@@ -193,14 +194,15 @@ def run_reference(args):
 def default_inflight(args):
     """shards proven concurrently per GPU: as many as the device memory comfortably holds (measured: ~17-24 GB per S2 context at the
     pool's high water mark; throughput saturates at 5-6 contexts), never more than 5"""
-    return args.inflight if args.inflight > 0 else {"S1": 5, "S2": 5, "S3": 3}.get(args.workload, 3)
+    return args.inflight if args.inflight > 0 else {"S1": 5, "S2": 5, "S1c": 5, "S2c": 5, "R1": 5, "tiny": 4, "tinyc": 4, "tinyr": 4}.get(args.workload, 3)
 
 
 def workload_config(workload, cells, cycles, n_chips, inflight):
     """the `config` object both arms print"""
-    padded = ((cells + (1 << 21) - 1) >> 21) << 21
+    ls = W.params_of(workload)["log_stacking_height"]
+    padded = ((cells + (1 << ls) - 1) >> ls) << ls
     c = {"workload": f"{workload}: {W.WORKLOADS[workload][1]}; main area {cells} cells = {cycles:.0f} cycles/shard "
-                     f"(cells/45), {n_chips} chips (synthetic AIR bytecode + LogUp interactions), {padded >> 21} stacked columns of 2^21, blowup 4, "
+                     f"(cells/45), {n_chips} chips (synthetic AIR bytecode + LogUp interactions), {padded >> ls} stacked columns of 2^{ls}, blowup 4, "
                      f"124 queries, 16+5+12 PoW bits",
          "phases": PHASES_DONE, "phases_not_yet_in_step": PHASES_MISSING}
     # identical in both arms (the driver compares the two config objects): the GPU-arm notes are stated for the GPU arm
@@ -272,6 +274,138 @@ def ref_kernels_leg(lib, n_cols, dev):
     return out
 
 
+def run_queue(args):
+    """--job queue (BASELINE config 5 / SURVEY.md 8e "S5"): `--shards` full shards with DISTINCT heights and traces (seeds 42+i) are
+    placed round-robin on the ranks (the reference's controller hands ProveShard tasks to free workers, crates/prover/src/worker/
+    client.rs:29-69), every rank's in-flight contexts pull their rank's shards from a host queue, each shard's trace goes H2D from
+    pinned memory through the upload slots, and all proofs are gathered to rank 0 (the input of the recursion tree) with one NCCL
+    gather - all inside the timed region.  Total work is fixed: strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from sp1_b200 import Lib
+    from sp1_b200 import shards as SH
+    from sp1_b200 import synth_air as SA
+    from sp1_b200.lib import HostChallenger
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N > 1)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_shards, distinct = args.shards, min(args.distinct, args.shards)
+    args.inflight = default_inflight(args)
+    base = W.synthetic_machine(args.workload, seed=42)
+    pv0 = 12345
+    pv = ((np.array([pv0, 5, 6, 7], dtype=np.uint64) << np.uint64(32)) % np.uint64(W.P)).astype(np.uint32)
+    # the distinct shard inputs this rank can be asked for: variant v = shard index % distinct (heights from seed 42+v)
+    mine = SH.shards_of_rank(n_shards, rank, world)
+    variants = sorted({i % distinct for i in mine})
+    h_traces, heights_of, cycles_of = {}, {}, {}
+    for v in variants:
+        mv = W.synthetic_machine(args.workload, seed=42 + v)
+        assert mv["names"] == base["names"] and [s_[1:] for s_ in mv["specs"]] == [s_[1:] for s_ in base["specs"]]
+        heights_of[v] = [s_[0] for s_ in mv["specs"]]
+        cycles_of[v] = W.area_of(mv["main_shapes"]) / W.CELLS_PER_CYCLE
+        parts = [SA.synth_trace_cuda(sp.h, sp.g, sp.wp, pv0, SH.shard_seed(42, v) + k, dev, extra_cols=sp.extra, extra_prep=sp.extra_prep)[0] for k, sp in enumerate(mv["specs"])]
+        d = torch.cat(parts)
+        h_traces[v] = torch.empty(d.shape, dtype=torch.int32, pin_memory=True)
+        h_traces[v].copy_(d)
+        del parts, d
+    # every variant's cycle count is needed for the total (a pure function of the seed)
+    per = {v: W.area_of(W.shard_shapes(args.workload, seed=42 + v)[1]) for v in range(distinct)}
+    pre_cells = W.area_of(base["main_shapes"]) - W.area_of(W.shard_shapes(args.workload, seed=42)[1])   # precompile table (same in every variant)
+    total_cycles = sum(per[i % distinct] + pre_cells for i in range(n_shards)) / W.CELLS_PER_CYCLE
+    # preprocessed tables are the same for every shard (their heights depend on the workload only)
+    preps = [SA.synth_trace_cuda(sp.h, sp.g, sp.wp, pv0, SH.shard_seed(0, 0) + k, dev, extra_cols=sp.extra, extra_prep=sp.extra_prep)[1] for k, sp in enumerate(base["specs"]) if sp.wp]
+    d_prep = torch.cat(preps).contiguous()
+    prep_rows = [s_.h for s_ in base["specs"] if s_.wp]
+    prep_cols = [1 + s_.extra_prep for s_ in base["specs"] if s_.wp]
+    torch.cuda.synchronize()
+    provers = []
+    for _ in range(args.inflight):
+        l_ = Lib(device=local, **W.params_of(args.workload))
+        m_ = l_.machine_create(base["blob"])
+        _, p_ = l_.jagged_commit_dense(d_prep, prep_rows, prep_cols)
+        provers.append((l_, m_, p_))
+    chal0 = HostChallenger().st.copy()
+    names = base["names"]
+
+    def worker(who, q, proofs, busy):
+        l_, m_, p_ = provers[who]
+        nxt = q.pop()
+        if nxt is None:
+            return
+        slot = 0
+        d_nxt = l_.upload_begin(h_traces[nxt % distinct], slot)
+        t0 = time.time()
+        while nxt is not None:
+            cur, d_cur = nxt, d_nxt
+            nxt = q.pop()
+            if nxt is not None:
+                slot ^= 1
+                d_nxt = l_.upload_begin(h_traces[nxt % distinct], slot)   # the next shard's H2D overlaps this shard's proof
+            st = chal0.copy()
+            proofs[cur] = l_.prove_shard(m_, p_, d_cur, heights_of[cur % distinct], names, pv, st)
+        busy[who] = time.time() - t0
+
+    def run_once(n):
+        q = SH.ShardQueue(n, rank, world)
+        proofs, busy = {}, [0.0] * len(provers)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        if world > 1:
+            dist.barrier()
+        for l_, _, _ in provers:
+            l_.sync()
+        torch.cuda.synchronize()
+        e0.record()
+        ths = [threading.Thread(target=worker, args=(w_, q, proofs, busy)) for w_ in range(len(provers))]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        for l_, _, _ in provers:
+            l_.sync()
+        e1.record()
+        allp = SH.gather_proofs(proofs, dst=0, device=dev)
+        torch.cuda.synchronize()
+        e2.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return e0.elapsed_time(e2), e1.elapsed_time(e2), allp, busy
+
+    run_once(min(n_shards, world * len(provers) * 2))   # slot allocation and pool growth are setup: one small untimed pass
+    with ClockSampler(local) as cs:
+        ms, gather_ms, allp, busy = run_once(n_shards)
+    clocks = cs.summary()
+    ms_all = SH.max_over_ranks(ms, dev)
+    launches = sum(l_.launch_count() for l_, _, _ in provers)
+    out = None
+    if rank == 0:
+        assert sorted(allp) == list(range(n_shards)), "rank 0 did not receive every shard's proof"
+        proof_bytes = int(sum(v.size for v in allp.values()) * 4)
+        h2d = int(sum(h_traces[i % distinct].numel() * 4 for i in mine))
+        v = total_cycles / (ms_all / 1e3)
+        out = {"metric": "riscv_cycles_proven_per_second_core", "value": v, "unit": "cycles/s", "n_gpus": world, "steps": 1, "warmup": 1,
+               "ms_per_step": ms_all, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "u32 KoalaBear (Montgomery) / ext4", "data": "synthetic", "job": "queue",
+               "config": {"workload": f"S5: {n_shards} shards of {args.workload} ({W.WORKLOADS[args.workload][1]}), {distinct} distinct height sets / traces "
+                                      f"(seeds 42+i), {total_cycles:.0f} cycles in total; round-robin over {world} rank(s), {len(provers)} contexts per rank "
+                                      "pulling from the rank's host queue; traces H2D per shard from pinned memory; proofs gathered to rank 0",
+                          "phases": PHASES_DONE, "l2": "working set exceeds L2"},
+               "e2e": {"value": v, "unit": "cycles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": proof_bytes,
+                       "note": "the job is end to end by construction: per-shard H2D, proof D2H and the gather are inside the timed region; "
+                               "h2d bytes are rank 0's"},
+               "gather": {"ms": gather_ms, "proof_bytes_total": proof_bytes, "how": "all_gather of the (index, length) table + one NCCL gather of padded words"},
+               "rank0_context_busy_s": [round(b, 3) for b in busy], "gpu_launches": int(launches), "clocks": clocks,
+               "limiter": "per-shard proving time; the queue is static across ranks (round-robin), so the slowest rank (most cells) sets the time; "
+                          "the gather is a few ms"}
+        print(json.dumps(out))
+    for l_, m_, p_ in provers:
+        l_.jagged_round_free(p_); l_.machine_free(m_); l_.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -290,9 +424,16 @@ def main():
                          "sumcheck tails of one shard overlap the NTT / Poseidon2 kernels of another")
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "serial"],
                     help="pipelined: H2D of step i+1 overlaps the proof of step i (upload slots); serial: plain host pointer per step")
+    ap.add_argument("--job", default="step", choices=["step", "queue"],
+                    help="step: the driver's contract (K identical steps, weak scaling); queue: --shards distinct shards through a host queue with "
+                         "per-shard H2D and a proof gather to rank 0 (strong scaling, BASELINE config 5)")
+    ap.add_argument("--shards", type=int, default=64)
+    ap.add_argument("--distinct", type=int, default=16, help="--job queue: number of distinct (heights, trace) sets the shards cycle over")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.job == "queue":
+        return run_queue(args)
 
     import torch
     import torch.distributed as dist
@@ -307,7 +448,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    lib = Lib(device=local)
+    params = W.params_of(args.workload)
+    lib = Lib(device=local, **params)
     stream = torch.cuda.ExternalStream(lib.stream(), device=dev)
 
     from sp1_b200 import synth_air as SA
@@ -322,10 +464,10 @@ def main():
     pv0 = 12345
     pv = ((np.array([pv0, 5, 6, 7], dtype=np.uint64) << np.uint64(32)) % np.uint64(W.P)).astype(np.uint32)
     mains, preps = [], []
-    for i, (h, g, wp, extra) in enumerate(specs):
-        m_, p_ = SA.synth_trace_cuda(h, g, wp, pv0, SH.shard_seed(0, my_shard) + i, dev, extra_cols=extra)
+    for i, sp in enumerate(specs):
+        m_, p_ = SA.synth_trace_cuda(sp.h, sp.g, sp.wp, pv0, SH.shard_seed(0, my_shard) + i, dev, extra_cols=sp.extra, extra_prep=sp.extra_prep)
         mains.append(m_)
-        if wp:
+        if sp.wp:
             preps.append(p_)
     d_main = torch.cat(mains).contiguous()
     d_prep = torch.cat(preps).contiguous()
@@ -335,20 +477,22 @@ def main():
     torch.cuda.synchronize()
     # setup (not timed; reference: AirProver::setup uploads the machine and commits the preprocessed traces once per program)
     machine = lib.machine_create(mach["blob"])
-    prep_rows = [s_[0] for s_ in specs if s_[2]]
-    _, h_prep = lib.jagged_commit_dense(d_prep, prep_rows, [1] * len(prep_rows))
+    prep_rows = [s_.h for s_ in specs if s_.wp]
+    prep_cols = [1 + s_.extra_prep for s_ in specs if s_.wp]
+    _, h_prep = lib.jagged_commit_dense(d_prep, prep_rows, prep_cols)
     # further in-flight provers on the same GPU: own context (stream, mailbox, upload slots), own machine / preprocessed commit
     # default: as many shards in flight as the device memory comfortably holds (measured: ~24 GB per S2 context at the pool's high
     # water mark; throughput saturates at 5-6 contexts), never more than 5
     args.inflight = default_inflight(args)
     provers = [(lib, machine, h_prep)]
     for _ in range(1, args.inflight):
-        l2 = Lib(device=local)
+        l2 = Lib(device=local, **params)
         m2 = l2.machine_create(mach["blob"])
-        _, p2 = l2.jagged_commit_dense(d_prep, prep_rows, [1] * len(prep_rows))
+        _, p2 = l2.jagged_commit_dense(d_prep, prep_rows, prep_cols)
         provers.append((l2, m2, p2))
     chal0 = HostChallenger().st.copy()
-    padded_cells = ((cells + (1 << 21) - 1) >> 21) << 21
+    LS = params["log_stacking_height"]
+    padded_cells = ((cells + (1 << LS) - 1) >> LS) << LS
 
     phase_names = ["commit.rs_encode", "commit.merkle", "merkle.leaf_hash", "shard.commit", "gkr.circuit", "gkr.rounds", "gkr.openings", "gkr.total", "gkr.host_wait", "gkr.host_interaction", "gkr.host_transcript",
                    "zerocheck.total", "zerocheck.host_wait", "zerocheck.host_math", "zerocheck.host_setup", "jagged.little_poly", "jagged.sumcheck", "jagged.eval_sumcheck", "open.batch", "open.fri_rounds",
@@ -441,11 +585,11 @@ def main():
     ach = 20.0 * padded_cells / (ntt_ms / 1e3) / 1e9
     merkle_ms = phases.get("commit.merkle", float("nan"))
     leaf_ms = phases.get("merkle.leaf_hash", float("nan"))
-    n_stacked = padded_cells >> 21
-    leaf_bytes = (4 * n_stacked + 32) * (1 << 23)
-    leaf_perms = (1 << 23) * ((n_stacked + 7) // 8)
+    n_stacked = padded_cells >> LS
+    leaf_bytes = (4 * n_stacked + 32) * (1 << (LS + 2))
+    leaf_perms = (1 << (LS + 2)) * ((n_stacked + 7) // 8)
     leaf_gbs = leaf_bytes / (leaf_ms / 1e3) / 1e9
-    perms = (1 << 23) * (((padded_cells >> 21) + 7) // 8) + (1 << 23)
+    perms = (1 << (LS + 2)) * ((n_stacked + 7) // 8) + (1 << (LS + 2))
     out = {
         "metric": "riscv_cycles_proven_per_second_core", "value": value, "unit": "cycles/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

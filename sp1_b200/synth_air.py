@@ -68,17 +68,19 @@ class Asm:
         return w
 
 
-def synth_chip(groups, with_prep, kconst=7, deep=False, n_constraints=None, extra_cols=0):
+def synth_chip(groups, with_prep, kconst=7, deep=False, n_constraints=None, extra_cols=0, extra_prep=0):
     """-> (machine words for this chip, main_w, prep_w).
     n_constraints (calibrated chips): further constraints of degree 2-3 are added round-robin over the groups until the chip has
     that many (at most 9 per group); each is implied by the template's relations, so the same traces satisfy them and they vanish on
     the all-zero padding row.  extra_cols: unconstrained filler columns after the template (exact reference widths, e.g. 682).
+    extra_prep (needs with_prep): further preprocessed columns; they are committed, opened and batched like any column but appear in
+    no constraint (recursion chips keep most of their columns preprocessed).
     deep=True emits the SAME constraints in an order with long-lived intermediates (all products a_g b_g first, consumed in
     reverse order afterwards): the register pressure of the program grows with `groups`, which exercises the larger
     register-file tiers of the zerocheck kernels (the flat order needs a handful of registers whatever the chip size)."""
     a = Asm()
     main_w = 6 * groups + (1 if with_prep else 0) + extra_cols
-    prep_w = 1 if with_prep else 0
+    prep_w = (1 + extra_prep) if with_prep else 0
     pv0 = a.public(0)
     kc = a.const(kconst)
     one = a.const(1)
@@ -131,7 +133,7 @@ def synth_chip(groups, with_prep, kconst=7, deep=False, n_constraints=None, extr
     return a.words(main_w, prep_w), main_w, prep_w
 
 
-def synth_trace(rng, height, groups, with_prep, pv0_canonical, kconst=7, extra_cols=0):
+def synth_trace(rng, height, groups, with_prep, pv0_canonical, kconst=7, extra_cols=0, extra_prep=0):
     """canonical-domain generation, returned as Montgomery words, column-major [w, height]"""
     cols = []
     prep = None
@@ -149,12 +151,12 @@ def synth_trace(rng, height, groups, with_prep, pv0_canonical, kconst=7, extra_c
     if with_prep:
         gcol = rng.integers(0, P, height, dtype=np.uint64)
         cols.append(gcol * a0 % P)
-        prep = to_monty(np.stack([gcol]))
+        prep = to_monty(np.stack([gcol] + [rng.integers(0, P, height, dtype=np.uint64) for _ in range(extra_prep)]))
     for _ in range(extra_cols):
         cols.append(rng.integers(0, P, height, dtype=np.uint64))
     main = to_monty(np.stack(cols)) if height else np.zeros((len(cols), 0), np.uint32)
     if with_prep and not height:
-        prep = np.zeros((1, 0), np.uint32)
+        prep = np.zeros((1 + extra_prep, 0), np.uint32)
     return main, prep
 
 
@@ -250,7 +252,7 @@ def machine_blob_with_interactions(chip_words, inter_words):
     return np.array(w, dtype=np.uint32)
 
 
-def synth_trace_cuda(height, groups, with_prep, pv0_canonical, seed, device, kconst=7, extra_cols=0):
+def synth_trace_cuda(height, groups, with_prep, pv0_canonical, seed, device, kconst=7, extra_cols=0, extra_prep=0):
     """same trace family generated on the GPU with torch (bench input only): -> (main [w*height] int32 Montgomery words
     column-major, prep [height] or None)"""
     import torch
@@ -280,6 +282,8 @@ def synth_trace_cuda(height, groups, with_prep, pv0_canonical, seed, device, kco
         gc = torch.randint(0, P, (height,), dtype=torch.int64, device=device, generator=g)
         out[6 * groups] = mont(gc * a0 % P)
         prep = mont(gc)
+        if extra_prep:
+            prep = torch.cat([prep] + [mont(torch.randint(0, P, (height,), dtype=torch.int64, device=device, generator=g)) for _ in range(extra_prep)])
     for j in range(extra_cols):
         out[6 * groups + (1 if with_prep else 0) + j] = mont(torch.randint(0, P, (height,), dtype=torch.int64, device=device, generator=g))
     return out.reshape(-1), prep

@@ -5,9 +5,14 @@ the core machine's cost table (crates/core/executor/src/artifacts/rv64im_costs.j
 (crates/hypercube/src/util.rs:57) up to 2^22 filling a target area, values uniform field elements, zero padding.
 cycles := cells / 45 for synthetic inputs.  Test / bench input generation only: no prover logic here.
 """
+import collections
+
 import numpy as np
 
 P = 0x7F000001
+# one chip of a synthetic machine: height, 6-column constraint groups, has preprocessed columns, filler main columns, further
+# preprocessed columns (synth_air.synth_chip / synth_trace take exactly these)
+Spec = collections.namedtuple("Spec", "h g wp extra extra_prep")
 CELLS_PER_CYCLE = 45
 
 # main-trace chips of the core cluster and their total column counts (rv64im_costs.json, v6.4.0)
@@ -36,7 +41,27 @@ WORKLOADS = {
     "S3p": (402_653_184, "full shard, 30 % of the area in a 682-column precompile table (keccak-permute-like), light chips"),
     "S3c": (402_653_184, "full shard, 30 % of the area in a 682-column precompile table, calibrated chips"),
     "tinyc": (1 << 21, "smoke-sized shard, calibrated chips + a small precompile table"),
+    # compress-shape shard (BASELINE config 5 "core+compress"): the recursion machine's eight chips, most columns
+    # preprocessed, ~2^27 cells, RECURSION protocol parameters (crates/verifier/src/compressed/config.rs:1-2, fri_params.rs:20-26)
+    "R1": (1 << 27, "compress-shape shard: recursion machine (8 chips, preprocessed-heavy), 2^27 main cells, stacking 2^20, rows <= 2^21"),
+    "tinyr": (1 << 20, "smoke-sized compress-shape shard"),
 }
+# protocol parameters per workload family: core = crates/prover/src/components.rs:16-17 + core_fri_config, recursion =
+# RECURSION_LOG_STACKING_HEIGHT / RECURSION_MAX_LOG_ROW_COUNT + recursion_fri_config (same blowup 2 -> 124 queries, 16 PoW bits)
+CORE_PARAMS = dict(log_stacking_height=21, max_log_row_count=22)
+RECURSION_PARAMS = dict(log_stacking_height=20, max_log_row_count=21)
+
+
+def params_of(workload):
+    return dict(RECURSION_PARAMS if workload in RECURSION_WORKLOADS else CORE_PARAMS)
+
+
+RECURSION_WORKLOADS = {"R1", "tinyr"}
+# compress machine (crates/recursion/machine/src/machine.rs:89-105), in name order: (name, main width, preprocessed width, share of the
+# main area).  Widths are APPROXIMATE (the column structs' sizes need rustc): what matters for the prover is the shape - a wide
+# Poseidon2 table that dominates the area, narrow ALU / memory tables at full height, most columns preprocessed.
+RECURSION_CHIPS = [("BaseAlu", 7, 8, 0.10), ("ExtAlu", 13, 8, 0.16), ("MemoryConst", 7, 4, 0.04), ("MemoryVar", 7, 8, 0.10),
+                   ("Poseidon2Wide", 157, 36, 0.50), ("PrefixSumChecks", 19, 8, 0.04), ("PublicValues", 7, 16, 0.0), ("Select", 7, 10, 0.06)]
 PRECOMPILE = ("KeccakPermute", 682)       # 682-wide precompile columns
 PRECOMPILE_SHARE = {"S3p": 0.30, "S3c": 0.30, "tinyc": 0.30}
 CALIBRATED = {"S1c", "S2c", "S3c", "tinyc"}
@@ -112,6 +137,8 @@ def synthetic_machine(workload, seed=42, max_log_rows=22, scale=1.0):
     down by `scale` (CPU baseline sample).  Calibrated workloads take each chip's constraint count and interaction message
     lengths from chip_stats.json."""
     from . import synth_air as SA
+    if workload in RECURSION_WORKLOADS:
+        return _recursion_machine(workload, seed, scale)
     prep, main = shard_shapes(workload, seed=seed, max_log_rows=max_log_rows)
     calibrated = workload in CALIBRATED
     stats = chip_stats() if calibrated else {}
@@ -132,7 +159,7 @@ def synthetic_machine(workload, seed=42, max_log_rows=22, scale=1.0):
         h = int(rows * scale) // 32 * 32 if rows else 0
         if rows and not h:
             h = 32
-        names.append(name); specs.append((h, g, wp, extra))
+        names.append(name); specs.append(Spec(h, g, wp, extra, 0))
         st = stats.get(name) if calibrated else None
         if name == PRECOMPILE[0] and calibrated:
             # a permutation precompile: ~2 constraints per column, a handful of wide memory / syscall interactions
@@ -147,6 +174,29 @@ def synthetic_machine(workload, seed=42, max_log_rows=22, scale=1.0):
         words.append(cw)
         iwords.append(iw)
     blob = SA.machine_blob_with_interactions(words, iwords)
-    main_shapes = [(h, 6 * g + (1 if wp else 0) + extra) for h, g, wp, extra in specs]
-    prep_shapes = [(h, 1) for h, g, wp, extra in specs if wp]
+    return _machine_dict(names, specs, blob)
+
+
+def _machine_dict(names, specs, blob):
+    main_shapes = [(s.h, 6 * s.g + (1 if s.wp else 0) + s.extra) for s in specs]
+    prep_shapes = [(s.h, 1 + s.extra_prep) for s in specs if s.wp]
     return dict(names=names, specs=specs, blob=blob, main_shapes=main_shapes, prep_shapes=prep_shapes)
+
+
+def _recursion_machine(workload, seed, scale):
+    """compress-shape machine: RECURSION_CHIPS with heights (multiples of 32, <= 2^21) that give each chip its share of the main area"""
+    from . import synth_air as SA
+    area = WORKLOADS[workload][0]
+    rng = np.random.default_rng(seed)
+    names, specs, words, iwords = [], [], [], []
+    for name, mw, pw, share in sorted(RECURSION_CHIPS):
+        g = max(1, (mw - 1) // 6)
+        extra = mw - 1 - 6 * g
+        rows = 32 if share == 0.0 else min(int(share * area * (0.9 + 0.2 * rng.random()) / mw) // 32 * 32, 1 << RECURSION_PARAMS["max_log_row_count"])
+        h = max(32, int(rows * scale) // 32 * 32)
+        names.append(name); specs.append(Spec(h, g, True, extra, pw - 1))
+        cw, _, _ = SA.synth_chip(g, True, n_constraints=min(9 * g, 6 * g), extra_cols=extra, extra_prep=pw - 1)
+        words.append(cw)
+        # recursion chips talk to the memory argument only: a few 5-value (address, extension value) messages per row
+        iwords.append(SA.synth_interactions_calibrated(g, True, [5] * min(2 * g, 12)))
+    return _machine_dict(names, specs, SA.machine_blob_with_interactions(words, iwords))

@@ -58,8 +58,8 @@ def fullsize_inputs(workload, seed):
     mach = W.synthetic_machine(workload, seed=42)
     rng = np.random.default_rng(seed)
     mains, preps = [], []
-    for h, g, wp, extra in mach["specs"]:
-        m_, p_ = SA.synth_trace(rng, h, g, wp, FULL_PV0, extra_cols=extra)
+    for sp in mach["specs"]:
+        m_, p_ = SA.synth_trace(rng, sp.h, sp.g, sp.wp, FULL_PV0, extra_cols=sp.extra, extra_prep=sp.extra_prep)
         mains.append(m_); preps.append(p_)
     pv = O.to_monty(np.array([FULL_PV0, 5, 6, 7]))
     ch = O.Challenger()

@@ -26,22 +26,22 @@ def test_synthetic_machine_is_consistent():
     m = W.synthetic_machine("tiny", seed=42)
     assert m["names"] == sorted(m["names"])
     assert len(m["names"]) == len(m["specs"]) == len(m["main_shapes"])
-    for (h, g, wp, extra), (rows, cols) in zip(m["specs"], m["main_shapes"]):
-        assert rows == h and cols == 6 * g + (1 if wp else 0) + extra
+    for sp, (rows, cols) in zip(m["specs"], m["main_shapes"]):
+        assert rows == sp.h and cols == 6 * sp.g + (1 if sp.wp else 0) + sp.extra
     assert int(m["blob"][0]) == len(m["specs"])
     small = W.synthetic_machine("S2", seed=42, scale=1 / 64)
     assert W.area_of(small["main_shapes"]) < W.area_of(W.synthetic_machine("S2", seed=42)["main_shapes"]) / 32
 
 
-@pytest.mark.parametrize("workload", ["tiny", "tinyc"])
+@pytest.mark.parametrize("workload", ["tiny", "tinyc", "tinyr"])
 def test_synthetic_traces_satisfy_constraints_and_interactions(workload):
     """a scaled-down copy of the bench machine (light and calibrated + precompile table): the oracle proves it and its restated
     verifier accepts (constraints hold on every real row, the LogUp cumulative sum is zero)"""
     m = W.synthetic_machine(workload, seed=42, scale=1 / 256)
     rng = np.random.default_rng(3)
     mains, preps = [], []
-    for h, g, wp, extra in m["specs"]:
-        a, p = SA.synth_trace(rng, h, g, wp, 12345, extra_cols=extra)
+    for sp in m["specs"]:
+        a, p = SA.synth_trace(rng, sp.h, sp.g, sp.wp, 12345, extra_cols=sp.extra, extra_prep=sp.extra_prep)
         mains.append(a); preps.append(p)
     pv = O.to_monty(np.array([12345, 5, 6, 7]))
     heights = [s_[0] for s_ in m["specs"]]

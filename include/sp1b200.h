@@ -241,6 +241,24 @@ sp1b200_err sp1b200_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* machine
                                 const uint32_t* h_public_values, uint32_t n_public_values, const uint32_t* h_replay_witnesses,
                                 uint32_t* h_challenger34, uint32_t* h_proof, uint64_t proof_cap_words, uint64_t* h_proof_words);
 
+/* AirProver::setup_and_prove_shard (crates/hypercube/src/prover/shard.rs:56-68), the vk-less path: setup (commit the preprocessed
+ * traces = the device part of the proving key), observe the verifying key, prove the shard.
+ * prep_dense_any / h_prep_rows / h_prep_cols (n_prep tables): as sp1b200_jagged_commit, the tables of the chips with preprocessed columns
+ * in chip order.  The verifying key enters a FRESH transcript the way MachineVerifyingKey::observe_into does
+ * (crates/hypercube/src/verifier/config.rs:97-112): the preprocessed commitment (8 words, produced here) followed by h_vk_tail - the
+ * words the shim builds from the program: pc_start[3], initial_global_cumulative_sum x[7] y[7], enable_untrusted_programs, six zero
+ * padding words - so h_challenger34 is the state BEFORE the key is observed (sp1b200_challenger_init for a new proof).
+ * h_prep_commit8 receives the commitment (MachineVerifyingKey::preprocessed_commit); *prep_round_out receives the committed round
+ * (keep it for later sp1b200_prove_shard calls of the same program, free it with sp1b200_jagged_round_free).  Everything else as
+ * sp1b200_prove_shard. */
+sp1b200_err sp1b200_setup_and_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* machine, const uint32_t* prep_dense_any, uint32_t n_prep,
+                                          const uint64_t* h_prep_rows, const uint64_t* h_prep_cols, const uint32_t* h_vk_tail,
+                                          uint32_t n_vk_tail, const uint32_t* main_dense_any, const uint64_t* h_heights,
+                                          const char* const* chip_names, const uint32_t* h_public_values, uint32_t n_public_values,
+                                          const uint32_t* h_replay_witnesses, uint32_t* h_challenger34, uint32_t* h_prep_commit8,
+                                          sp1b200_jagged_round** prep_round_out, uint32_t* h_proof, uint64_t proof_cap_words,
+                                          uint64_t* h_proof_words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@
 //   machine()                       -> the chips (name order) this prover was built for
 //   setup_from_vk(...)              -> commits the preprocessed traces once per program, returns the proving key
 //                                      (`PreprocessedData<ProvingKey>`) and the preprocessed commitment of the verifying key
+//   setup_and_prove_shard(...)      -> setup, observe the verifying key, prove (the vk-less path of the first shard of a program)
 //   prove_shard_with_pk(pk, record) -> the shard proof for one execution record (here: its main traces in the dense layout)
 //   preprocessed_table_heights(pk)  -> chip name -> height of its preprocessed table
 // The reference implementations are infallible by signature and panic on failure (worker maps the panic to TaskError::Fatal);
@@ -142,6 +143,35 @@ class AirProver {
         check(sp1b200_prove_shard(ctx_, machine_, pk.round_, main_dense_any, heights.data(), names.data(), public_values.data(),
                                   (uint32_t)public_values.size(), replay_witnesses, challenger.data(), proof_buf_.data(), kCapWords, &n));
         return std::vector<uint32_t>(proof_buf_.begin(), proof_buf_.begin() + n);
+    }
+
+    // AirProver::setup_and_prove_shard (shard.rs:56-68): setup + MachineVerifyingKey::observe_into + prove in one call.
+    // `challenger` is the transcript BEFORE the verifying key is observed; vk_tail = the words observed after the preprocessed
+    // commitment (pc_start[3], initial_global_cumulative_sum x[7] y[7], enable_untrusted_programs, six zeros; config.rs:97-112).
+    // Returns (proving key - its commit is the vk's preprocessed_commit -, proof words).
+    std::pair<ProvingKey, std::vector<uint32_t>> setup_and_prove_shard(const uint32_t* prep_dense_any, const uint32_t* main_dense_any,
+                                                                       const std::vector<uint64_t>& heights, const std::vector<uint32_t>& vk_tail,
+                                                                       const std::vector<uint32_t>& public_values, Challenger& challenger,
+                                                                       const uint32_t* replay_witnesses = nullptr) {
+        if (heights.size() != chips_.size()) throw Error("setup_and_prove_shard: one height per chip expected");
+        std::vector<uint64_t> rows, cols;
+        std::vector<const char*> names;
+        ProvingKey pk;
+        for (size_t k = 0; k < chips_.size(); k++) {
+            names.push_back(chips_[k].name.c_str());
+            if (chips_[k].preprocessed_width) {
+                rows.push_back(heights[k]); cols.push_back(chips_[k].preprocessed_width);
+                pk.heights[chips_[k].name] = heights[k];
+            }
+        }
+        pk.ctx_ = ctx_;
+        if (proof_buf_.size() < kCapWords) proof_buf_.resize(kCapWords);
+        uint64_t n = 0;
+        check(sp1b200_setup_and_prove_shard(ctx_, machine_, prep_dense_any, (uint32_t)rows.size(), rows.data(), cols.data(), vk_tail.data(),
+                                            (uint32_t)vk_tail.size(), main_dense_any, heights.data(), names.data(), public_values.data(),
+                                            (uint32_t)public_values.size(), replay_witnesses, challenger.data(), pk.commit.data(), &pk.round_,
+                                            proof_buf_.data(), kCapWords, &n));
+        return {std::move(pk), std::vector<uint32_t>(proof_buf_.begin(), proof_buf_.begin() + n)};
     }
 
     sp1b200_ctx* context() const { return ctx_; }

@@ -192,6 +192,89 @@ __global__ void __launch_bounds__(256) hadamard_fold0_kernel(SegTable base, cons
     block_reduce2(s0, sh, partial, mail);
 }
 
+// ---- round 0 without the materialised little polynomial ("factored" path) -------------------------------------------------------
+// ext[i] = col_eq[c(i)] * row_eq[i - prefix[c]] is a product of two small tables (2^11 and 2^22 entries), so when every column
+// start is even (all heights even: the reference pads heights to multiples of 32, crates/hypercube/src/util.rs:57) a pair (2j, 2j+1)
+// lies in one column and
+//   sum_j ext[2j] b[2j]                       = sum_c col_eq[c] * sum_{j in c} row_eq[r_j] b[2j]
+//   sum_j (ext[2j]+ext[2j+1]) (b[2j]+b[2j+1]) = sum_c col_eq[c] * sum_{j in c} (row_eq[r_j]+row_eq[r_j+1]) (b[2j]+b[2j+1])
+// with base-field b: the inner sums cost EF x F products only and the 2^log_m-entry EF polynomial (4.3 GB for a 2^22-cycle shard) is
+// never written or read.  Every warp walks a contiguous span of pairs, lanes keep running sums for their current column and
+// multiply by col_eq[c] only when the column changes.  The fold by alpha keeps the product form:
+//   ext'[o] = col_eq[c(2o)] * row_eq'[(2o - prefix[c]) / 2],   row_eq'[k] = row_eq[2k] + alpha (row_eq[2k+1] - row_eq[2k]).
+__device__ __forceinline__ uint32_t jp_column(const uint64_t* __restrict__ prefix, uint32_t ncols, uint32_t c, uint64_t i) {
+    while (c + 1 < ncols && prefix[c + 1] <= i) c++;
+    return c;
+}
+__global__ void __launch_bounds__(256) row_eq_fold_kernel(const uint32_t* __restrict__ row_eq, Ext alpha, uint64_t n_out, uint32_t* __restrict__ out) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_out) return;
+    const Ext a = kb::ext_load(row_eq + 8 * k), b = kb::ext_load(row_eq + 8 * k + 4);
+    kb::ext_store(out + 4 * k, kb::ext_add(a, kb::ext_mul(alpha, kb::ext_sub(b, a))));
+}
+__global__ void __launch_bounds__(256) hadamard_sum0_fused_kernel(SegTable base, const uint64_t* __restrict__ prefix, uint32_t ncols,
+                                                                  const uint32_t* __restrict__ start, const uint32_t* __restrict__ col_eq,
+                                                                  const uint32_t* __restrict__ row_eq, uint64_t npairs_real, uint64_t span,
+                                                                  uint32_t* __restrict__ partial, Mail mail) {
+    Ext s0 = kb::ext_zero(), sh = kb::ext_zero();
+    Ext t0 = kb::ext_zero(), th = kb::ext_zero();
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t j_begin = warp * span, j_end = min(j_begin + span, npairs_real);
+    uint32_t c = 0xffffffffu;
+    for (uint64_t j = j_begin + lane; j < j_end; j += 32) {
+        const uint64_t i = 2 * j;
+        const uint32_t cn = jp_column(prefix, ncols, c == 0xffffffffu ? start[i >> JP_SHIFT] : c, i);
+        if (cn != c) {
+            if (c != 0xffffffffu) {
+                const Ext ce = kb::ext_load(col_eq + 4 * c);
+                s0 = kb::ext_add(s0, kb::ext_mul(ce, t0)); sh = kb::ext_add(sh, kb::ext_mul(ce, th));
+                t0 = kb::ext_zero(); th = kb::ext_zero();
+            }
+            c = cn;
+        }
+        const uint32_t b0 = seg_load(base, i), b1 = seg_load(base, i + 1);
+        const uint64_t r = i - prefix[c];
+        const Ext e0 = kb::ext_load(row_eq + 4 * r), e1 = kb::ext_load(row_eq + 4 * r + 4);
+        t0 = kb::ext_add(t0, kb::ext_mul_base(e0, b0));
+        th = kb::ext_add(th, kb::ext_mul_base(kb::ext_add(e0, e1), kb::add(b0, b1)));
+    }
+    if (c != 0xffffffffu) {
+        const Ext ce = kb::ext_load(col_eq + 4 * c);
+        s0 = kb::ext_add(s0, kb::ext_mul(ce, t0)); sh = kb::ext_add(sh, kb::ext_mul(ce, th));
+    }
+    block_reduce2(s0, sh, partial, mail);
+}
+// fix the last variable of round 0 in product form and accumulate round-1 sums; roweq2 = row_eq folded by alpha (row_eq_fold_kernel)
+__global__ void __launch_bounds__(256) hadamard_fold0_fused_kernel(SegTable base, const uint64_t* __restrict__ prefix, uint32_t ncols,
+                                                                   const uint32_t* __restrict__ start, const uint32_t* __restrict__ col_eq,
+                                                                   const uint32_t* __restrict__ roweq2, uint64_t area, uint64_t nout_pairs, Ext alpha,
+                                                                   uint32_t* __restrict__ base_out, uint32_t* __restrict__ ext_out,
+                                                                   uint32_t* __restrict__ partial, uint64_t nout, Mail mail) {
+    Ext s0 = kb::ext_zero(), sh = kb::ext_zero();
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nout_pairs; j += (uint64_t)gridDim.x * blockDim.x) {
+        Ext nb[2], ne[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint64_t o = 2 * j + h;  // output index; inputs 2o, 2o+1
+            if (o < nout) {
+                const uint64_t i = 2 * o;
+                const uint32_t b0 = seg_load(base, i), b1 = seg_load(base, i + 1);
+                nb[h] = kb::ext_add(kb::ext_from_base(b0), kb::ext_mul_base(alpha, kb::sub(b1, b0)));
+                if (i < area) {
+                    const uint32_t c = jp_column(prefix, ncols, start[i >> JP_SHIFT], i);
+                    ne[h] = kb::ext_mul(kb::ext_load(col_eq + 4 * c), kb::ext_load(roweq2 + 4 * ((i - prefix[c]) >> 1)));
+                } else ne[h] = kb::ext_zero();
+                kb::ext_store(base_out + 4 * o, nb[h]);
+                kb::ext_store(ext_out + 4 * o, ne[h]);
+            } else { nb[h] = kb::ext_zero(); ne[h] = kb::ext_zero(); }
+        }
+        s0 = kb::ext_add(s0, kb::ext_mul(ne[0], nb[0]));
+        sh = kb::ext_add(sh, kb::ext_mul(kb::ext_add(ne[0], ne[1]), kb::ext_add(nb[0], nb[1])));
+    }
+    block_reduce2(s0, sh, partial, mail);
+}
+
 // rounds >= 1: fix the last variable (EF -> EF) and accumulate the next round's sums
 __global__ void __launch_bounds__(256) hadamard_fold_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ ext,
                                                             uint64_t nout_pairs, Ext alpha, uint32_t* __restrict__ base_out,
@@ -625,7 +708,17 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
     uint32_t* d_jp_start;
     SP1_TRY(mem.alloc((void**)&d_jp_start, jp_start.size() * 4));
     SP1_CUDA(cudaMemcpyAsync(d_jp_start, jp_start.data(), jp_start.size() * 4, cudaMemcpyHostToDevice, st));
-    SP1_TRY(mem.alloc((void**)&d_ext, N * 16));
+    // factored round 0 (no materialised little polynomial) whenever every column starts at an even index
+    bool factored = lm >= 2;
+    for (uint64_t p : prefix) factored = factored && (p & 1) == 0;
+    { static const bool off = [] { const char* e = getenv("SP1B200_JAGGED_MATERIALISE"); return e && e[0] == '1'; }(); if (off) factored = false; }
+    uint32_t* d_roweq2 = nullptr;
+    if (factored) {
+        SP1_TRY(mem.alloc((void**)&d_ext, (N / 4 + 1) * 16));          // only from round 2 on
+        SP1_TRY(mem.alloc((void**)&d_roweq2, ((size_t)16) << (mlr - 1)));
+    } else {
+        SP1_TRY(mem.alloc((void**)&d_ext, N * 16));
+    }
     SP1_TRY(mem.alloc((void**)&d_ext2, (N / 2) * 16));
     SP1_TRY(mem.alloc((void**)&d_b, (N / 2) * 16));
     SP1_TRY(mem.alloc((void**)&d_b2, (N / 4 + 1) * 16));
@@ -634,7 +727,7 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
     d_partial = sp1b200_mail_dev(ctx);  // the round kernels post their block partials straight into the mailbox
     {
         PhaseTimer t(ctx, "jagged.little_poly");
-        SP1_LAUNCH(ctx, jagged_poly_kernel, blocks_for(N), 256, 0, d_prefix, (uint32_t)total_cols, d_jp_start, d_coleq, d_roweq, N, d_ext);
+        if (!factored) SP1_LAUNCH(ctx, jagged_poly_kernel, blocks_for(N), 256, 0, d_prefix, (uint32_t)total_cols, d_jp_start, d_coleq, d_roweq, N, d_ext);
         t.stop();
     }
     SegTable seg{};
@@ -657,7 +750,15 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
         if (rd == 0) {
             g = grid_for(n / 2);
             const Mail mail = sp1b200_mail_next(ctx);
-            SP1_LAUNCH(ctx, hadamard_sum0_kernel, g, 256, 0, seg, cur_e, n / 2, d_partial, mail);
+            if (factored) {
+                // contiguous span of pairs per warp (multiple of 32), over the real area only (beyond it the polynomial is zero)
+                const uint64_t pairs_real = prefix.back() / 2, warps = (uint64_t)g * 8;
+                const uint64_t span = (((pairs_real + warps - 1) / warps) + 31) / 32 * 32;
+                SP1_LAUNCH(ctx, hadamard_sum0_fused_kernel, g, 256, 0, seg, d_prefix, (uint32_t)total_cols, d_jp_start, d_coleq, d_roweq, pairs_real,
+                           span ? span : 32, d_partial, mail);
+            } else {
+                SP1_LAUNCH(ctx, hadamard_sum0_kernel, g, 256, 0, seg, cur_e, n / 2, d_partial, mail);
+            }
             SP1_TRY(sum_mail(ctx, mail.seq, g, e0, eh));
         } else {
             SP1_TRY(sum_mail(ctx, prev_seq, prev_g, e0, eh));  // accumulated by the previous fold launch
@@ -678,8 +779,14 @@ sp1b200_err sp1b200_jagged_prove(sp1b200_ctx* ctx, sp1b200_jagged_round* const* 
         g = grid_for((nout + 1) / 2);
         const Mail mail = sp1b200_mail_next(ctx); prev_seq = mail.seq;
         if (rd == 0) {
-            SP1_LAUNCH(ctx, hadamard_fold0_kernel, g, 256, 0, seg, cur_e, (nout + 1) / 2, da, nxt_b, nxt_e, d_partial, nout, mail);
-            cur_b = nxt_b; cur_e = nxt_e; nxt_b = d_b2; nxt_e = d_ext;  // d_ext (N entries) is free again
+            if (factored) {
+                SP1_LAUNCH(ctx, row_eq_fold_kernel, blocks_for((uint64_t)1 << (mlr - 1)), 256, 0, d_roweq, da, (uint64_t)1 << (mlr - 1), d_roweq2);
+                SP1_LAUNCH(ctx, hadamard_fold0_fused_kernel, g, 256, 0, seg, d_prefix, (uint32_t)total_cols, d_jp_start, d_coleq, d_roweq2, prefix.back(),
+                           (nout + 1) / 2, da, nxt_b, nxt_e, d_partial, nout, mail);
+            } else {
+                SP1_LAUNCH(ctx, hadamard_fold0_kernel, g, 256, 0, seg, cur_e, (nout + 1) / 2, da, nxt_b, nxt_e, d_partial, nout, mail);
+            }
+            cur_b = nxt_b; cur_e = nxt_e; nxt_b = d_b2; nxt_e = d_ext;  // d_ext is free again (materialised path) / sized for round 2 on
         } else {
             SP1_LAUNCH(ctx, hadamard_fold_kernel, g, 256, 0, cur_b, cur_e, (nout + 1) / 2, da, nxt_b, nxt_e, d_partial, nout, mail);
             std::swap(cur_b, nxt_b); std::swap(cur_e, nxt_e);

@@ -152,4 +152,33 @@ sp1b200_err sp1b200_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* m, sp1b
     }
     return nullptr;
 }
+
+// AirProver::setup_and_prove_shard (shard.rs:56-68): setup = commit the preprocessed traces, observe the verifying key
+// (MachineVerifyingKey::observe_into, verifier/config.rs:97-112: commitment, then the program-dependent words), prove.
+sp1b200_err sp1b200_setup_and_prove_shard(sp1b200_ctx* ctx, const sp1b200_machine* m, const uint32_t* prep_dense_any, uint32_t n_prep,
+                                          const uint64_t* h_prep_rows, const uint64_t* h_prep_cols, const uint32_t* h_vk_tail, uint32_t n_vk_tail,
+                                          const uint32_t* main_dense_any, const uint64_t* h_heights, const char* const* chip_names,
+                                          const uint32_t* h_pv, uint32_t n_pv, const uint32_t* h_replay_witnesses, uint32_t* h_chal,
+                                          uint32_t* h_prep_commit8, sp1b200_jagged_round** prep_round_out, uint32_t* h_proof, uint64_t cap,
+                                          uint64_t* h_words) { SP1_DEVICE_GUARD(ctx);
+    if (!prep_round_out) return sp1b200_set_error("setup_and_prove_shard: prep_round_out is NULL");
+    *prep_round_out = nullptr;
+    uint32_t commit[8] = {0};
+    sp1b200_jagged_round* prep = nullptr;
+    if (n_prep) SP1_TRY(sp1b200_jagged_commit(ctx, prep_dense_any, n_prep, h_prep_rows, h_prep_cols, 1, commit, &prep));
+    HostChallenger ch;
+    sp1b200_err e = ch.init(ctx, h_chal);
+    if (!e) {
+        ch.observe_n(commit, 8);
+        ch.observe_n(h_vk_tail, n_vk_tail);
+        uint32_t st[34];
+        ch.store(st);
+        e = sp1b200_prove_shard(ctx, m, prep, main_dense_any, h_heights, chip_names, h_pv, n_pv, h_replay_witnesses, st, h_proof, cap, h_words);
+        if (!e) memcpy(h_chal, st, sizeof(st));
+    }
+    if (e) { sp1b200_jagged_round_free(ctx, prep); return e; }
+    if (h_prep_commit8) memcpy(h_prep_commit8, commit, 32);
+    *prep_round_out = prep;
+    return nullptr;
+}
 }

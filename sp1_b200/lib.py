@@ -58,6 +58,7 @@ ERR_FUNCS = [
     "sp1b200_memcpy_d2h", "sp1b200_upload_begin", "sp1b200_pack_row_major", "sp1b200_poseidon2_permute", "sp1b200_rs_encode", "sp1b200_merkle_commit", "sp1b200_grind",
     "sp1b200_stacked_commit", "sp1b200_stacked_prove", "sp1b200_jagged_commit", "sp1b200_jagged_column_claims",
     "sp1b200_jagged_prove", "sp1b200_machine_create", "sp1b200_zerocheck", "sp1b200_logup_gkr", "sp1b200_prove_shard",
+    "sp1b200_setup_and_prove_shard",
 ]
 OTHER_FUNCS = ["sp1b200_challenger_init", "sp1b200_challenger_observe", "sp1b200_challenger_sample",
                "sp1b200_challenger_sample_bits", "sp1b200_challenger_check_witness", "sp1b200_ctx_destroy", "sp1b200_default_core_params", "sp1b200_version", "sp1b200_ctx_stream",
@@ -258,6 +259,28 @@ class Lib:
         self._chk(self.L.sp1b200_prove_shard(self.ctx, machine, prep_round, _ptr(main_dense), H, NM, _ptr(pv), C.c_uint32(pv.size),
                                              _ptr(rw), _ptr(challenger_state), _ptr(out), C.c_uint64(cap_words), C.byref(nw)))
         return out[:nw.value].copy()
+
+    def setup_and_prove_shard(self, machine, prep_dense, prep_rows, prep_cols, vk_tail, main_dense, heights, names, pv, challenger_state,
+                              replay=None, cap_words=1 << 24):
+        """AirProver::setup_and_prove_shard: -> (prep_commit[8], prep_round handle, proof words); challenger_state = the state BEFORE
+        the verifying key is observed, updated in place"""
+        n = len(heights)
+        H = (C.c_uint64 * n)(*heights)
+        NM = (C.c_char_p * n)(*[s.encode() for s in names])
+        npz = len(prep_rows)
+        R = (C.c_uint64 * max(1, npz))(*prep_rows)
+        Cc = (C.c_uint64 * max(1, npz))(*prep_cols)
+        pv = np.ascontiguousarray(pv, dtype=np.uint32)
+        tail = np.ascontiguousarray(vk_tail, dtype=np.uint32)
+        out = np.empty(cap_words, np.uint32)
+        nw = C.c_uint64()
+        pc = np.zeros(8, np.uint32)
+        h = C.c_void_p()
+        rw = None if replay is None else np.ascontiguousarray(replay, dtype=np.uint32)
+        self._chk(self.L.sp1b200_setup_and_prove_shard(self.ctx, machine, _ptr(prep_dense), C.c_uint32(npz), R, Cc, _ptr(tail), C.c_uint32(tail.size),
+                                                       _ptr(main_dense), H, NM, _ptr(pv), C.c_uint32(pv.size), _ptr(rw), _ptr(challenger_state),
+                                                       _ptr(pc), C.byref(h), _ptr(out), C.c_uint64(cap_words), C.byref(nw)))
+        return pc, h, out[:nw.value].copy()
 
     def pack_row_major(self, rows_any, shapes, d_dense_out):
         """tables back to back, each row-major [rows x cols] -> device buffer with each table column-major"""

@@ -122,3 +122,43 @@ def test_prove_shard_replays_non_minimal_witnesses(skip):
     lib.jagged_round_free(prep_round)
     lib.machine_free(mach)
     lib.close()
+
+
+def test_setup_and_prove_shard_equals_setup_then_prove():
+    """AirProver::setup_and_prove_shard (shard.rs:56-68): one call = commit the preprocessed traces, observe the verifying key the way
+    MachineVerifyingKey::observe_into does (commitment, then the program words), prove.  Must equal the three steps done by hand, and the
+    oracle's proof from the same post-vk transcript."""
+    from sp1_b200 import Lib
+    from sp1_b200.lib import HostChallenger
+    spec = [(1024, 2, True), (256 + 32, 3, False), (0, 1, False), (2048, 1, True)]
+    log_stack, mlr, nq, pw, bpw, gpw = 10, 11, 8, 4, 2, 3
+    rng = np.random.default_rng(8080)
+    blob, heights, mains, preps, pv = _synth_machine_gkr(rng, spec)
+    names = [f"Chip{i:02d}" for i in range(len(heights))]
+    vk_tail = np.concatenate([O.rand_field(rng, 3 + 7 + 7), O.to_monty(np.array([0])), np.zeros(6, np.uint32)])   # pc_start, cumulative sum x, y, flag, padding
+    lib = Lib(0, log_stacking_height=log_stack, max_log_row_count=mlr, num_queries=nq, pow_bits=pw, batch_pow_bits=bpw, gkr_pow_bits=gpw)
+    mach = lib.machine_create(blob)
+    prep_tabs = [p for p in preps if p is not None]
+    prep_dense = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(p).reshape(-1) for p in prep_tabs]))
+    rows, cols = [p.shape[1] for p in prep_tabs], [p.shape[0] for p in prep_tabs]
+    dense = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(m).reshape(-1) for m in mains if m.size]))
+    st = HostChallenger().st.copy()
+    pc, prep_round, words = lib.setup_and_prove_shard(mach, prep_dense, rows, cols, vk_tail, dense, heights, names, pv, st)
+    # by hand
+    pc2, round2 = lib.jagged_commit(prep_tabs)
+    hc = HostChallenger()
+    hc.observe(pc2); hc.observe(vk_tail)
+    post_vk = hc.st.copy()
+    st2 = post_vk.copy()
+    words2 = lib.prove_shard(mach, round2, dense, heights, names, pv, st2)
+    assert (pc == pc2).all() and (words == words2).all() and (st == st2).all()
+    # the returned round is the proving key: a second shard of the same program proves against it
+    words3 = lib.prove_shard(mach, prep_round, dense, heights, names, pv, post_vk.copy())
+    assert (words3 == words).all()
+    och = O.Challenger(); och.st[:] = post_vk
+    opc, owords = O.prove_shard_verify(blob, heights, mains, preps, names, pv, log_stack, mlr, och, num_queries=nq, pow_bits=pw,
+                                       batch_pow_bits=bpw, gkr_pow_bits=gpw)
+    assert (opc == pc).all() and (owords == words).all() and (och.st == st).all()
+    lib.jagged_round_free(prep_round); lib.jagged_round_free(round2)
+    lib.machine_free(mach)
+    lib.close()

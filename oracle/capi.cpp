@@ -402,6 +402,69 @@ static void put(std::vector<uint32_t>& o, const GkrProof& p) {
     put(o, p.witness);
 }
 
+// ---- primitives exported so that tests can pin them to the reference's own CUDA kernels (oracle/_ref) ----------------------------------
+// First-layer LogUp fractions of ONE chip (execution.rs:13-36; reference kernel: populateLastCircuitLayer / interactionValue,
+// sys/lib/logup_gkr/tracegen.cu:20-75): out_num[k * height + r] = multiplicity (negated for receives), out_den[(k * height + r) * 4 ..] =
+// alpha + betas[0] * arg_index + sum_j betas[j + 1] * value_j, for interaction k and row r.
+int64_t orc_interaction_values(const uint32_t* machine_blob, uint32_t chip, const uint32_t* main, const uint32_t* prep, uint64_t height,
+                               const uint32_t* alpha4, const uint32_t* betas, uint32_t n_betas, uint32_t* out_num, uint32_t* out_den) {
+    const uint32_t* rest;
+    std::vector<MachineChip> mc = parse_machine(machine_blob, &rest);
+    auto inter = parse_interactions(rest, mc.size());
+    if (chip >= mc.size()) return -1;
+    const EF alpha = EF::from_base_slice(asF(alpha4));
+    std::vector<EF> bs(n_betas);
+    for (uint32_t i = 0; i < n_betas; i++) bs[i] = EF::from_base_slice(asF(betas + 4 * i));
+    const auto& I = inter[chip];
+    std::vector<F> mr(mc[chip].main_w), pr(mc[chip].prep_w);
+    for (uint64_t r = 0; r < height; r++) {
+        for (size_t j = 0; j < mr.size(); j++) mr[j] = F::raw(main[j * height + r]);
+        for (size_t j = 0; j < pr.size(); j++) pr[j] = F::raw(prep[j * height + r]);
+        for (size_t k = 0; k < I.size(); k++) {
+            if (I[k].values.size() + 1 > bs.size()) return -2;
+            auto [m, d] = interaction_vals<F>(I[k], pr.data(), mr.data(), alpha, bs);
+            out_num[k * height + r] = m.v;
+            for (int l = 0; l < 4; l++) out_den[(k * height + r) * 4 + l] = d.c[l].v;
+        }
+    }
+    return (int64_t)I.size();
+}
+
+// Zerocheck round-0 node sums of ONE chip's constraint program (sum_as_poly.rs:225-286; reference kernel: zerocheck_fused_sequential,
+// sys/lib/zerocheck/sequential.cu:110-190): out[t] = sum_i E[i] * sum_k powers[alpha_idx_k] * reg_k evaluated on the row pair
+// (2i, 2i+1) interpolated at the nodes {0, 2, 4} - no opening-batching term, no geq / padded-row correction, lambda = 1.
+int64_t orc_zerocheck_node_sums(const uint32_t* machine_blob, uint32_t chip, const uint32_t* main, const uint32_t* prep, uint64_t height,
+                                const uint32_t* pv_words, uint32_t n_pv, const uint32_t* alpha_pows, const uint32_t* E, uint32_t* out12) {
+    std::vector<MachineChip> mc = parse_machine(machine_blob);
+    if (chip >= mc.size() || (height & 1)) return -1;
+    const AirProgram& air = mc[chip].air;
+    const size_t mw = mc[chip].main_w, pw = mc[chip].prep_w;
+    std::vector<F> pv(n_pv);
+    for (uint32_t i = 0; i < n_pv; i++) pv[i] = F::raw(pv_words[i]);
+    std::vector<EF> pw_(air.n_constraints ? air.n_constraints : 1);
+    for (size_t i = 0; i < air.n_constraints; i++) pw_[i] = EF::from_base_slice(asF(alpha_pows + 4 * i));
+    EF y[3];
+    std::vector<F> m0(mw), m2(mw), m4(mw), p0(pw), p2(pw), p4(pw), regs;
+    for (uint64_t i = 0; i < height / 2; i++) {
+        for (size_t c = 0; c < mw; c++) {
+            F a = F::raw(main[c * height + 2 * i]), b = F::raw(main[c * height + 2 * i + 1]);
+            F sl = b - a, sl2 = sl + sl;
+            m0[c] = a; m2[c] = sl2 + a; m4[c] = sl2 + sl2 + a;
+        }
+        for (size_t c = 0; c < pw; c++) {
+            F a = F::raw(prep[c * height + 2 * i]), b = F::raw(prep[c * height + 2 * i + 1]);
+            F sl = b - a, sl2 = sl + sl;
+            p0[c] = a; p2[c] = sl2 + a; p4[c] = sl2 + sl2 + a;
+        }
+        const EF e = EF::from_base_slice(asF(E + 4 * i));
+        y[0] += eval_air<F>(air, p0.data(), m0.data(), pv.data(), pw_.data(), regs) * e;
+        y[1] += eval_air<F>(air, p2.data(), m2.data(), pv.data(), pw_.data(), regs) * e;
+        y[2] += eval_air<F>(air, p4.data(), m4.data(), pv.data(), pw_.data(), regs) * e;
+    }
+    for (int t = 0; t < 3; t++) for (int l = 0; l < 4; l++) out12[4 * t + l] = y[t].c[l].v;
+    return 0;
+}
+
 // ---- LogUp-GKR stand-alone: prove + restated verify_logup_gkr.  Words out: n_out | numerator[n_out] | denominator[n_out] |
 // n_rounds | per round {numerator_0 numerator_1 denominator_0 denominator_1 sumcheck} | point | per chip {main openings, prep openings} | witness
 int64_t orc_gkr_prove_verify(const uint32_t* machine_blob, const uint64_t* heights, const uint32_t* const* main, const uint32_t* const* prep,

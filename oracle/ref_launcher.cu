@@ -20,6 +20,8 @@
 #include "challenger/challenger.cuh"
 #include "basefold/basefold.cuh"
 #include "mle/mle.cuh"
+#include "logup_gkr/tracegen.cuh"
+#include "zerocheck/sequential.cuh"
 #include "runtime/exception.cuh"
 
 // sys/include/ntt/sppark.cuh (definitions live in lib/ntt/sppark.cu; prototypes restated: sys/src/dft.rs:5-50)
@@ -389,4 +391,132 @@ const char* ref_challenger_script(uint32_t* st34, const uint32_t* ops, const uin
     return ch.read(st34);
 }
 
+
+// ---- LogUp-GKR first layer: the reference's interaction evaluation ------------------------------------------------------------------
+// populateLastCircuitLayer (sys/lib/logup_gkr/tracegen.cu:77-160) for ONE chip.  The interactions arrive in the flattened CSR form of
+// `Interactions<F>` (sys/include/logup_gkr/tracegen.cuh:20-36; host twin sp1-gpu/crates/logup_gkr/src/interactions.rs).  Output layout as
+// the kernel writes it: with q = ceil(ceil(height/2)/2), interaction j owns the row-pair slots [2 q j, 2 q j + ceil(height/2)); slot i
+// holds (numerator at row 2i, denominator at row 2i) and, 2 * output_height further, the same for row 2i+1; output_height = 2 q n.
+extern "C" void* logup_gkr_populate_last_circuit_layer();
+const char* ref_gkr_populate(const uint32_t* h_prep, uint64_t prep_words, const uint32_t* h_main, uint64_t main_words, uint64_t height, uint32_t n_inter,
+                             const uint64_t* values_ptr, const uint64_t* mult_ptr, const uint64_t* vcw_ptr, uint64_t n_values, const uint64_t* vcw_col,
+                             const uint8_t* vcw_is_prep, const uint32_t* vcw_weight, uint64_t n_vcw, const uint32_t* values_constants,
+                             const uint64_t* mcw_col, const uint8_t* mcw_is_prep, const uint32_t* mcw_weight, uint64_t n_mcw,
+                             const uint32_t* mult_constants, const uint32_t* arg_indices, const uint8_t* is_send, const uint32_t* alpha4,
+                             const uint32_t* betas, uint32_t n_betas, uint32_t* out_num, uint32_t* out_den, uint64_t* out_height) {
+    const uint64_t half = height ? (height + 1) / 2 : 1, q = (half + 1) / 2, outH = 2 * q * n_inter;
+    auto up = [](const void* h, size_t bytes, void** d) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, bytes ? bytes : 8);
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+        return e;
+    };
+    std::vector<PairCol<felt_t>> vcw(n_vcw), mcw(n_mcw);
+    for (uint64_t i = 0; i < n_vcw; i++) { vcw[i].column_idx = vcw_col[i]; vcw[i].is_preprocessed = vcw_is_prep[i]; memcpy(&vcw[i].weight, &vcw_weight[i], 4); }
+    for (uint64_t i = 0; i < n_mcw; i++) { mcw[i].column_idx = mcw_col[i]; mcw[i].is_preprocessed = mcw_is_prep[i]; memcpy(&mcw[i].weight, &mcw_weight[i], 4); }
+    std::vector<uint8_t> send(is_send, is_send + n_inter);   // bool on the device side
+    std::vector<uint32_t> start(n_inter + 1);
+    for (uint32_t j = 0; j <= n_inter; j++) start[j] = (uint32_t)(q * j);
+    Interactions<felt_t> I{};
+    void *d_prep, *d_main, *d_start, *d_col, *d_num, *d_den, *d_betas;
+    RCHK(up(values_ptr, (n_inter + 1) * 8, (void**)&I.values_ptr));
+    RCHK(up(mult_ptr, (n_inter + 1) * 8, (void**)&I.multiplicities_ptr));
+    RCHK(up(vcw_ptr, (n_values + 1) * 8, (void**)&I.values_col_weights_ptr));
+    RCHK(up(vcw.data(), n_vcw * sizeof(PairCol<felt_t>), (void**)&I.values_col_weights));
+    RCHK(up(values_constants, n_values * 4, (void**)&I.values_constants));
+    RCHK(up(mcw.data(), n_mcw * sizeof(PairCol<felt_t>), (void**)&I.mult_col_weights));
+    RCHK(up(mult_constants, n_inter * 4, (void**)&I.mult_constants));
+    RCHK(up(arg_indices, n_inter * 4, (void**)&I.arg_indices));
+    RCHK(up(send.data(), n_inter, (void**)&I.is_send));
+    I.num_interactions = n_inter;
+    RCHK(up(h_prep, prep_words * 4, &d_prep));
+    RCHK(up(h_main, main_words * 4, &d_main));
+    RCHK(up(start.data(), start.size() * 4, &d_start));
+    RCHK(up(betas, (size_t)n_betas * 16, &d_betas));
+    RCHK(cudaMalloc(&d_col, (2 * outH + 8) * 4));
+    RCHK(cudaMalloc(&d_num, 4 * outH * 4 + 16));
+    RCHK(cudaMalloc(&d_den, 4 * outH * 16 + 16));
+    RCHK(cudaMemset(d_num, 0, 4 * outH * 4 + 16));
+    RCHK(cudaMemset(d_den, 0, 4 * outH * 16 + 16));
+    Ext4Raw alpha;
+    memcpy(&alpha, alpha4, 16);
+    size_t offset = 0, th = height, oh = outH;
+    bool is_padding = false;
+    void* args[] = {&I, &d_start, &d_col, &d_num, &d_den, &d_prep, &d_main, &alpha, &d_betas, &offset, &th, &oh, &is_padding};
+    dim3 block(64, 4), grid((unsigned)((half + 63) / 64), (n_inter + 3) / 4);
+    RCHK(cudaLaunchKernel(logup_gkr_populate_last_circuit_layer(), grid, block, args, 0, 0));
+    RCHK(cudaDeviceSynchronize());
+    RCHK(cudaMemcpy(out_num, d_num, 4 * outH * 4, cudaMemcpyDeviceToHost));
+    RCHK(cudaMemcpy(out_den, d_den, 4 * outH * 16, cudaMemcpyDeviceToHost));
+    *out_height = outH;
+    for (void* p : {(void*)I.values_ptr, (void*)I.multiplicities_ptr, (void*)I.values_col_weights_ptr, (void*)I.values_col_weights, (void*)I.values_constants,
+                    (void*)I.mult_col_weights, (void*)I.mult_constants, (void*)I.arg_indices, (void*)I.is_send, d_prep, d_main, d_start, d_col, d_num, d_den, d_betas})
+        cudaFree(p);
+    return nullptr;
+}
+
+// ---- zerocheck: the reference's constraint-bytecode interpreter ----------------------------------------------------------------------
+// zerocheck_fused_sequential<felt_t, 1024> (sys/lib/zerocheck/sequential.cu:110-190) over ONE chip = one chunk: per block the sum over its
+// row pairs of eq[pair] * sum_k powers_of_alpha[alpha_idx_k] * reg_k at the node blockIdx.z of {0, 2, 4}, times powers_of_lambda[chip].
+// trace = main columns then preprocessed columns (column-major, even height).  out12 = the three node sums (ext each); the per-block
+// partials are added on the device with the reference's own kb31_extension_t addition (thin kernel below).
+__global__ void ref_sum_partials_kernel(const kb31_extension_t* partials, uint32_t n_blocks, kb31_extension_t* out3) {
+    if (blockIdx.x || threadIdx.x >= 3) return;
+    kb31_extension_t acc = kb31_extension_t::zero();
+    for (uint32_t b = 0; b < n_blocks; b++) acc += partials[b * 3 + threadIdx.x];
+    out3[threadIdx.x] = acc;
+}
+const char* ref_zerocheck_node_sums(const uint32_t* h_instrs, uint32_t n_instrs, const uint32_t* h_leaves, uint32_t n_leaves, const uint32_t* h_consts,
+                                    uint32_t n_consts, const uint32_t* h_publics, uint32_t n_publics, const uint32_t* h_assert_regs,
+                                    const uint32_t* h_assert_alphas, uint32_t n_asserts, const uint32_t* h_main, uint32_t main_w,
+                                    const uint32_t* h_prep, uint32_t prep_w, uint32_t height, const uint32_t* h_pv, uint32_t n_pv,
+                                    const uint32_t* h_alpha_pows, uint32_t n_alpha, const uint32_t* h_E, uint32_t log_pairs, uint32_t* out12) {
+    if (height & 1) return "ref_zerocheck_node_sums: even heights only (the kernel reads rows 2i and 2i+1)";
+    auto up = [](const void* h, size_t bytes, void** d) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, bytes ? bytes : 8);
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+        return e;
+    };
+    std::vector<uint16_t> regs16(n_asserts);
+    for (uint32_t i = 0; i < n_asserts; i++) regs16[i] = (uint16_t)h_assert_regs[i];
+    ChunkStatic st{};
+    void *d_trace, *d_pv, *d_ap, *d_E, *d_lambda, *d_gkr, *d_disp, *d_st, *d_lay, *d_part, *d_out;
+    RCHK(up(h_instrs, (size_t)n_instrs * 8, (void**)&st.instrs));
+    RCHK(up(h_leaves, (size_t)n_leaves * 8, (void**)&st.leaves));
+    RCHK(up(h_consts, (size_t)n_consts * 4, (void**)&st.consts));
+    RCHK(up(h_publics, (size_t)n_publics * 4, (void**)&st.publics));
+    RCHK(up(regs16.data(), (size_t)n_asserts * 2, (void**)&st.assert_regs));
+    RCHK(up(h_assert_alphas, (size_t)n_asserts * 4, (void**)&st.assert_alphas));
+    st.n_instrs = n_instrs; st.n_asserts = n_asserts; st.chip_idx = 0; st.gkr_main_width = 0; st.gkr_prep_width = 0; st.chip_alpha_offset = 0;
+    std::vector<uint32_t> trace((size_t)(main_w + prep_w) * height);
+    memcpy(trace.data(), h_main, (size_t)main_w * height * 4);
+    if (prep_w) memcpy(trace.data() + (size_t)main_w * height, h_prep, (size_t)prep_w * height * 4);
+    ChipLayout lay{0, (uint64_t)main_w * height, height, 0};
+    const uint32_t pairs = height / 2, tile = 1024, n_blocks = (pairs + tile - 1) / tile;
+    std::vector<BlockDispatch> disp(n_blocks ? n_blocks : 1);
+    for (uint32_t b = 0; b < n_blocks; b++) disp[b] = BlockDispatch{0, b * tile, (b + 1) * tile <= pairs ? tile : pairs - b * tile};
+    const uint32_t one[4] = {0x01fffffeu, 0, 0, 0};
+    RCHK(up(trace.data(), trace.size() * 4, &d_trace));
+    RCHK(up(h_pv, (size_t)n_pv * 4, &d_pv));
+    RCHK(up(h_alpha_pows, (size_t)n_alpha * 16, &d_ap));
+    RCHK(up(h_E, ((size_t)16) << log_pairs, &d_E));
+    RCHK(up(one, 16, &d_lambda));
+    RCHK(up(one, 16, &d_gkr));
+    RCHK(up(disp.data(), disp.size() * sizeof(BlockDispatch), &d_disp));
+    RCHK(up(&st, sizeof st, &d_st));
+    RCHK(up(&lay, sizeof lay, &d_lay));
+    RCHK(cudaMalloc(&d_part, (size_t)(n_blocks ? n_blocks : 1) * 3 * 16));
+    RCHK(cudaMalloc(&d_out, 3 * 16));
+    uint32_t dim = log_pairs;
+    void* args[] = {&d_disp, &d_st, &d_lay, &d_trace, &d_pv, &d_ap, &d_E, &d_lambda, &d_gkr, &dim, &d_part};
+    if (n_blocks) RCHK(cudaLaunchKernel(zerocheck_fused_sequential_kb_1024_kernel(), dim3(n_blocks, 1, 3), dim3(256), args, (256 / 32) * 16, 0));
+    ref_sum_partials_kernel<<<1, 32>>>((const kb31_extension_t*)d_part, n_blocks, (kb31_extension_t*)d_out);
+    RCHK(cudaGetLastError());
+    RCHK(cudaMemcpy(out12, d_out, 48, cudaMemcpyDeviceToHost));
+    for (void* p : {(void*)st.instrs, (void*)st.leaves, (void*)st.consts, (void*)st.publics, (void*)st.assert_regs, (void*)st.assert_alphas, d_trace, d_pv, d_ap,
+                    d_E, d_lambda, d_gkr, d_disp, d_st, d_lay, d_part, d_out})
+        cudaFree(p);
+    return nullptr;
+}
+
 }  // extern "C"
+

@@ -14,6 +14,7 @@
 // Step B runs in place on the step-A output of the same column group while it is still L2-resident
 // (B200: 126 MB L2; one 2^23-row column is 32 MB), so the intermediate never costs an HBM round trip.
 #include "ctx.cuh"
+#include <cstdlib>
 #include "kb31.cuh"
 
 namespace {
@@ -206,8 +207,9 @@ __global__ void __launch_bounds__(256) rs_step_b_2048(uint32_t* __restrict__ buf
 // ---- fast step A: tile of 8 consecutive lo x all 2^L1 hi, L1 = 3*NP + 1, 2^L1 threads ----------------------
 __device__ __forceinline__ int swzA(int e) { return e ^ (((e >> 7) & 1) << 4); }
 
-template <int L1>
-__global__ void __launch_bounds__(1 << L1) rs_step_a_fast(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int L2, int b,
+// MINB = 2 caps the kernel at 32 registers (9 words spill to local memory) so that two 1024-thread blocks share an SM
+template <int L1, int MINB = 1>
+__global__ void __launch_bounds__(1 << L1, MINB) rs_step_a_fast(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int L2, int b,
                                                           const uint32_t* __restrict__ TH, const uint32_t* __restrict__ TL) {
     static_assert(L1 % 3 == 1 && L1 >= 7, "L1 = 3k+1, at least two radix-8 passes");
     constexpr int NP = L1 / 3;           // radix-8 passes; the last stage (hi bit 0) is a warp shuffle
@@ -274,12 +276,12 @@ __global__ void __launch_bounds__(1 << L1) rs_step_a_fast(const uint32_t* __rest
 
 }  // namespace
 
-template <int L1>
+template <int L1, int MINB = 1>
 static sp1b200_err launch_step_a_fast(sp1b200_ctx* ctx, const uint32_t* in, uint32_t* out, int L2, int b, unsigned nc) {
     const size_t smem = 2 * (size_t)(8 << L1) * sizeof(uint32_t);
-    SP1_CUDA(cudaFuncSetAttribute(rs_step_a_fast<L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SP1_CUDA(cudaFuncSetAttribute(rs_step_a_fast<L1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g((1u << L2) / 8, nc);
-    SP1_LAUNCH(ctx, rs_step_a_fast<L1>, g, 1 << L1, smem, in, out, L2, b, ctx->d_TH, ctx->d_TL);
+    SP1_LAUNCH(ctx, (rs_step_a_fast<L1, MINB>), g, 1 << L1, smem, in, out, L2, b, ctx->d_TH, ctx->d_TL);
     return nullptr;
 }
 
@@ -321,7 +323,11 @@ sp1b200_err sp1b200_rs_encode_device(sp1b200_ctx* ctx, const uint32_t* d_msg, ui
     for (uint64_t c0 = 0; c0 < ncols; c0 += group) {
         unsigned nc = (unsigned)((ncols - c0 < group) ? (ncols - c0) : group);
         dim3 gA((1u << L2) / T, nc), gB(1u << (L1 + b), nc);
-        if (fast && L1 == 10) SP1_TRY(launch_step_a_fast<10>(ctx, d_msg + c0 * n, d_out + c0 * M, L2, b, nc));
+        // two 1024-thread blocks per SM (32 registers, 9 words of spill) measured 7.42 ms against 7.79 ms for the 52-register build on
+        // the 95 columns of S2 (profiles/bench_r02_occ*.json); SP1B200_RS_A_OCC2=0 selects the one-block build
+        static const bool occ2 = [] { const char* e = getenv("SP1B200_RS_A_OCC2"); return !(e && e[0] == '0'); }();
+        if (fast && L1 == 10 && occ2) SP1_TRY((launch_step_a_fast<10, 2>(ctx, d_msg + c0 * n, d_out + c0 * M, L2, b, nc)));
+        else if (fast && L1 == 10) SP1_TRY(launch_step_a_fast<10>(ctx, d_msg + c0 * n, d_out + c0 * M, L2, b, nc));
         else if (fast && L1 == 7) SP1_TRY(launch_step_a_fast<7>(ctx, d_msg + c0 * n, d_out + c0 * M, L2, b, nc));
         else SP1_LAUNCH(ctx, rs_step_a_generic, gA, threadsA, smemA, d_msg + c0 * n, d_out + c0 * M, L1, L2, b, T, ctx->d_TH, ctx->d_TL);
         if (fast) SP1_LAUNCH(ctx, rs_step_b_2048, gB, 256, 0, d_out + c0 * M, L1, b, ctx->d_TH, ctx->d_TL);

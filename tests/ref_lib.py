@@ -33,7 +33,7 @@ def lib():
         L = C.CDLL(SO)
         for n in ("ref_init", "ref_malloc", "ref_free", "ref_h2d", "ref_d2h", "ref_field_op", "ref_ext_op", "ref_permute", "ref_hash",
                   "ref_compress", "ref_merkle_tree", "ref_batch_coset_dft", "ref_batch", "ref_fold_mle_ext", "ref_fix_last_variable_ext",
-                  "ref_partial_lagrange_ext", "ref_grind", "ref_challenger_script"):
+                  "ref_partial_lagrange_ext", "ref_grind", "ref_challenger_script", "ref_gkr_populate", "ref_zerocheck_node_sums"):
             getattr(L, n).restype = C.c_char_p
         _chk(L.ref_init())
         _lib = L
@@ -235,3 +235,117 @@ def challenger_script(st34, ops, vals):
     out = np.zeros(ops.size, np.uint32)
     _chk(lib().ref_challenger_script(_p(st), _p(ops), _p(vals), _p(out), C.c_size_t(ops.size)))
     return st, out
+
+
+# ---- machine-blob parsing (the product's blob format, include/sp1b200.h) for the reference's own data layouts ---------------------------
+def parse_chip_words(blob):
+    """-> list of dicts per chip {main_w, prep_w, n_constraints, n_regs, instrs, leaves, consts, publics, assert_regs, assert_alphas}, and
+    the offset where the interaction section starts"""
+    b = np.asarray(blob, np.uint32)
+    n = int(b[0]); o = 1
+    chips = []
+    for _ in range(n):
+        main_w, prep_w, n_c, n_regs, ni, nl, nc, npub, na = [int(x) for x in b[o:o + 9]]; o += 9
+        c = dict(main_w=main_w, prep_w=prep_w, n_constraints=n_c, n_regs=n_regs)
+        c["instrs"] = b[o:o + 2 * ni].copy(); o += 2 * ni
+        c["leaves"] = b[o:o + 2 * nl].copy(); o += 2 * nl
+        c["consts"] = b[o:o + nc].copy(); o += nc
+        c["publics"] = b[o:o + npub].copy(); o += npub
+        c["assert_regs"] = b[o:o + na].copy(); o += na
+        c["assert_alphas"] = b[o:o + na].copy(); o += na
+        chips.append(c)
+    return chips, o
+
+
+def parse_interactions(blob, offset, n_chips):
+    """-> per chip: list of (is_send, arg_index, mult vcol, [value vcols]); vcol = (constant, [(source, col, weight)])"""
+    b = np.asarray(blob, np.uint32); o = offset
+    out = []
+
+    def vcol():
+        nonlocal o
+        nt, const = int(b[o]), int(b[o + 1]); o += 2
+        terms = [(int(b[o + 3 * t]), int(b[o + 3 * t + 1]), int(b[o + 3 * t + 2])) for t in range(nt)]
+        o += 3 * nt
+        return const, terms
+    for _ in range(n_chips):
+        n = int(b[o]); o += 1
+        chip = []
+        for _ in range(n):
+            is_send, arg, nv = int(b[o]), int(b[o + 1]), int(b[o + 2]); o += 3
+            mult = vcol()
+            vals = [vcol() for _ in range(nv)]
+            chip.append((is_send, arg, mult, vals))
+        out.append(chip)
+    return out
+
+
+def gkr_populate(inter, main, prep, alpha, betas):
+    """the reference's populateLastCircuitLayer for one chip.  inter: one chip of parse_interactions; main / prep: [w, h] column-major.
+    -> (num [n_inter, h] uint32, den [n_inter, h, 4])"""
+    LEAF_PREP = 2
+    h = main.shape[1]
+    n = len(inter)
+    values_ptr, mult_ptr, vcw_ptr = [0], [0], [0]
+    vcw, mcw, vconst, mconst, args, send = [], [], [], [], [], []
+    for is_send, arg, (mc, mterms), vals in inter:
+        for const, terms in vals:
+            vconst.append(const)
+            vcw += [(col, src == LEAF_PREP, wt) for src, col, wt in terms]
+            vcw_ptr.append(len(vcw))
+        values_ptr.append(len(vconst))
+        mconst.append(mc)
+        mcw += [(col, src == LEAF_PREP, wt) for src, col, wt in mterms]
+        mult_ptr.append(len(mcw))
+        args.append(int(((arg << 32) % 0x7F000001)))
+        send.append(1 if is_send else 0)
+    u64 = lambda x: np.ascontiguousarray(np.array(x if len(x) else [0], dtype=np.uint64))
+    u32 = lambda x: np.ascontiguousarray(np.array(x if len(x) else [0], dtype=np.uint32))
+    u8 = lambda x: np.ascontiguousarray(np.array(x if len(x) else [0], dtype=np.uint8))
+    half = (h + 1) // 2 if h else 1
+    q = (half + 1) // 2
+    outH = 2 * q * n
+    num = np.zeros(4 * outH, np.uint32)
+    den = np.zeros((4 * outH, 4), np.uint32)
+    oh = C.c_uint64()
+    mainf = np.ascontiguousarray(main, np.uint32).reshape(-1)
+    prepf = np.ascontiguousarray(prep, np.uint32).reshape(-1) if prep is not None and prep.size else np.zeros(1, np.uint32)
+    a_vp, a_mp, a_vcp = u64(values_ptr), u64(mult_ptr), u64(vcw_ptr)
+    a_vc, a_vip, a_vw = u64([c for c, _, _ in vcw]), u8([p for _, p, _ in vcw]), u32([w for _, _, w in vcw])
+    a_mc, a_mip, a_mw = u64([c for c, _, _ in mcw]), u8([p for _, p, _ in mcw]), u32([w for _, _, w in mcw])
+    a_vconst, a_mconst, a_args, a_send = u32(vconst), u32(mconst), u32(args), u8(send)
+    alpha = np.ascontiguousarray(alpha, np.uint32); betas = np.ascontiguousarray(betas, np.uint32)
+    p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+    p8 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint8))
+    _chk(lib().ref_gkr_populate(_p(prepf), C.c_uint64(prepf.size if prep is not None and prep.size else 0), _p(mainf), C.c_uint64(mainf.size), C.c_uint64(h),
+                                C.c_uint32(n), p64(a_vp), p64(a_mp), p64(a_vcp), C.c_uint64(len(vconst)), p64(a_vc), p8(a_vip), _p(a_vw), C.c_uint64(len(vcw)),
+                                _p(a_vconst), p64(a_mc), p8(a_mip), _p(a_mw), C.c_uint64(len(mcw)), _p(a_mconst), _p(a_args), p8(a_send), _p(alpha),
+                                _p(betas.reshape(-1)), C.c_uint32(betas.shape[0]), _p(num), _p(den.reshape(-1)), C.byref(oh)))
+    assert oh.value == outH
+    out_num = np.zeros((n, h), np.uint32); out_den = np.zeros((n, h, 4), np.uint32)
+    for j in range(n):
+        base = 2 * q * j
+        out_num[j, 0::2] = num[base:base + half][: (h + 1) // 2]
+        out_num[j, 1::2] = num[base + 2 * outH:base + 2 * outH + half][: h // 2]
+        out_den[j, 0::2] = den[base:base + half][: (h + 1) // 2]
+        out_den[j, 1::2] = den[base + 2 * outH:base + 2 * outH + half][: h // 2]
+    return out_num, out_den
+
+
+def zerocheck_node_sums(chip, main, prep, pv, alpha_pows, E):
+    """the reference's zerocheck_fused_sequential<felt, 1024> over one chip (chip = one entry of parse_chip_words).  E: eq table over the
+    row PAIRS [2^k, 4].  -> [3, 4] sums at the nodes {0, 2, 4}"""
+    h = main.shape[1]
+    out = np.zeros(12, np.uint32)
+    mainf = np.ascontiguousarray(main, np.uint32).reshape(-1)
+    prepf = np.ascontiguousarray(prep, np.uint32).reshape(-1) if prep is not None and prep.size else np.zeros(1, np.uint32)
+    pw = 0 if prep is None else prep.shape[0]
+    pv = np.ascontiguousarray(pv, np.uint32); ap = np.ascontiguousarray(alpha_pows, np.uint32); E = np.ascontiguousarray(E, np.uint32)
+    k = E.shape[0].bit_length() - 1
+    z = lambda a: a if a.size else np.zeros(1, np.uint32)
+    _chk(lib().ref_zerocheck_node_sums(_p(z(chip["instrs"])), C.c_uint32(chip["instrs"].size // 2), _p(z(chip["leaves"])), C.c_uint32(chip["leaves"].size // 2),
+                                       _p(z(chip["consts"])), C.c_uint32(chip["consts"].size), _p(z(chip["publics"])), C.c_uint32(chip["publics"].size),
+                                       _p(z(chip["assert_regs"])), _p(z(chip["assert_alphas"])), C.c_uint32(chip["assert_regs"].size), _p(mainf),
+                                       C.c_uint32(main.shape[0]), _p(prepf), C.c_uint32(pw), C.c_uint32(h), _p(pv), C.c_uint32(pv.size), _p(ap.reshape(-1)),
+                                       C.c_uint32(ap.shape[0]), _p(E.reshape(-1)), C.c_uint32(k), _p(out)))
+    return out.reshape(3, 4)

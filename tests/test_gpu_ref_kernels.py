@@ -2,7 +2,9 @@
 oracle/_ref/libsp1ref.so by oracle/Makefile, launched with the reference's grid/block shapes by oracle/ref_launcher.cu) are run on
 the same seeded inputs as (a) the CPU oracle and (b) the product library through its C ABI.  Everything is bit-exact.
 Covers SURVEY.md §8 rows T1 (field, Poseidon2, sponge, compress, DuplexChallenger, grind), A3 (batch_coset_dft), A4 (leafHashPacked +
-compress tree) and the BaseFold / multilinear primitives of A5 (batchKernel, foldMle, fixLastVariable, partial_lagrange)."""
+compress tree), the BaseFold / multilinear primitives of A5 (batchKernel, foldMle, fixLastVariable, partial_lagrange), the LogUp-GKR
+first-layer interaction evaluation of A8 (populateLastCircuitLayer) and the zerocheck constraint-bytecode interpreter of A7
+(zerocheck_fused_sequential)."""
 import ctypes as C
 
 import numpy as np
@@ -230,3 +232,60 @@ def test_partial_lagrange_reference_vs_oracle(n_vars):
     exp = np.zeros((1 << n_vars, 4), np.uint32)
     O.lib().orc_partial_lagrange(O.ptr(point), C.c_uint64(n_vars), O.ptr(exp))
     assert (R.partial_lagrange_ext(point) == exp).all()
+
+
+@pytest.mark.parametrize("workload,chip_name,h", [("tinyc", "Add", 64), ("tinyc", "Byte", 96), ("tinyc", "DivRem", 32), ("tinyr", "ExtAlu", 128)])
+def test_gkr_interaction_values_reference_kernel_vs_oracle(workload, chip_name, h):
+    """populateLastCircuitLayer / interactionValue (sys/lib/logup_gkr/tracegen.cu:20-160) on a calibrated chip's interactions (4-9 values,
+    linear combinations of columns, preprocessed columns, constant and column multiplicities, sends and receives): numerator =
+    multiplicity (negated for receives), denominator = alpha + betas[0] arg_index + sum_j betas[j+1] value_j - exactly the oracle's
+    first GKR layer (crates/hypercube/src/logup_gkr/execution.rs:13-36 restated)"""
+    from sp1_b200 import synth_air as SA
+    from sp1_b200 import workload as W
+    m = W.synthetic_machine(workload, seed=42)
+    k = m["names"].index(chip_name)
+    sp = m["specs"][k]
+    rng = np.random.default_rng(77 + h)
+    main, prep = SA.synth_trace(rng, h, sp.g, sp.wp, 12345, extra_cols=sp.extra, extra_prep=sp.extra_prep)
+    chips, off = R.parse_chip_words(m["blob"])
+    inter = R.parse_interactions(m["blob"], off, len(chips))[k]
+    assert len(inter) >= 4
+    alpha = O.rand_field(rng, 4)
+    nb = 16
+    betas = O.rand_field(rng, (nb, 4))
+    rnum, rden = R.gkr_populate(inter, main, prep, alpha, betas)
+    onum = np.zeros((len(inter), h), np.uint32); oden = np.zeros((len(inter), h, 4), np.uint32)
+    prepf = np.ascontiguousarray(prep).reshape(-1) if prep is not None else np.zeros(1, np.uint32)
+    n = O.lib().orc_interaction_values(O.ptr(np.ascontiguousarray(m["blob"])), C.c_uint32(k), O.ptr(np.ascontiguousarray(main).reshape(-1)), O.ptr(prepf),
+                                       C.c_uint64(h), O.ptr(alpha), O.ptr(betas.reshape(-1)), C.c_uint32(nb), O.ptr(onum.reshape(-1)), O.ptr(oden.reshape(-1)))
+    assert n == len(inter)
+    assert (rnum == onum).all(), "LogUp numerators (multiplicities) differ from the reference kernel"
+    assert (rden == oden).all(), "LogUp denominators differ from the reference kernel"
+
+
+@pytest.mark.parametrize("workload,chip_name,h", [("tinyc", "Add", 64), ("tinyc", "Byte", 2048), ("tinyc", "Mul", 4096), ("tinyr", "Poseidon2Wide", 512)])
+def test_zerocheck_interpreter_reference_kernel_vs_oracle(workload, chip_name, h):
+    """zerocheck_fused_sequential<felt_t, 1024> (sys/lib/zerocheck/sequential.cu:49-190): the reference's own bytecode interpreter run on
+    this repository's chip programs (DagInstr / LeafRef / assert tables in the reference layout): opcode semantics, leaf sources,
+    public values, alpha-index lookup, node interpolation {0, 2, 4} and the eq weighting give the oracle's round-0 node sums"""
+    from sp1_b200 import synth_air as SA
+    from sp1_b200 import workload as W
+    m = W.synthetic_machine(workload, seed=42)
+    k = m["names"].index(chip_name)
+    sp = m["specs"][k]
+    rng = np.random.default_rng(99 + h)
+    main, prep = SA.synth_trace(rng, h, sp.g, sp.wp, 12345, extra_cols=sp.extra, extra_prep=sp.extra_prep)
+    chips, _ = R.parse_chip_words(m["blob"])
+    chip = chips[k]
+    pv = O.to_monty(np.array([12345, 5, 6, 7]))
+    alpha_pows = O.rand_field(rng, (max(1, chip["n_constraints"]), 4))    # any table: the kernel only indexes it
+    logp = max(1, (h // 2 - 1).bit_length())
+    E = O.rand_field(rng, (1 << logp, 4))
+    ref = R.zerocheck_node_sums(chip, main, prep, pv, alpha_pows, E)
+    exp = np.zeros(12, np.uint32)
+    prepf = np.ascontiguousarray(prep).reshape(-1) if prep is not None else np.zeros(1, np.uint32)
+    rc = O.lib().orc_zerocheck_node_sums(O.ptr(np.ascontiguousarray(m["blob"])), C.c_uint32(k), O.ptr(np.ascontiguousarray(main).reshape(-1)), O.ptr(prepf),
+                                         C.c_uint64(h), O.ptr(pv), C.c_uint32(pv.size), O.ptr(alpha_pows.reshape(-1)), O.ptr(E.reshape(-1)), O.ptr(exp))
+    assert rc == 0
+    assert (ref.reshape(-1) == exp).all(), "constraint interpreter node sums differ from the reference kernel"
+    assert ref.any()

@@ -68,3 +68,23 @@ def test_calibrated_machine_follows_the_chip_statistics():
     share = rows * cols / W.area_of(m["main_shapes"])
     assert 0.27 < share < 0.33
     assert abs(W.area_of(m["main_shapes"]) / W.WORKLOADS["S3c"][0] - 1) < 0.02
+
+
+def test_calibration_agrees_with_the_reference_recorded_gkr_workloads():
+    """reference-held data: sp1-gpu/crates/logup_gkr/layer_workloads.json lists the (chip, interaction) row counts of 119 real shards;
+    its interactions-per-chip distribution (summarised into chip_stats.json by tools/chip_stats.py) brackets what the static reading
+    of the Rust eval functions produced, and the calibrated S2c shard is at least as heavy as the heaviest recorded shard"""
+    import json
+    import os
+    st = json.load(open(os.path.join(os.path.dirname(W.__file__), "chip_stats.json")))
+    ref = st["reference_gkr_workloads"]
+    assert ref and ref["shards"] >= 100
+    per_chip = [v["interactions"] for k, v in st["chips"].items() if "interactions" in v and k in dict(W.CORE_CHIPS)]
+    med = sorted(per_chip)[len(per_chip) // 2]
+    assert ref["interactions_per_chip"]["p10"] <= med <= ref["interactions_per_chip"]["p90"]
+    m = W.synthetic_machine("S2c", seed=42)
+    heavy = 0
+    for name, sp in zip(m["names"], m["specs"]):
+        v = st["chips"].get(name, {}).get("values_per_interaction", [4] * 8)
+        heavy += sp.h * (2 * len(v[::2]) + (2 if sp.wp else 0))
+    assert heavy >= ref["sum_rows_times_interactions"]["max"]

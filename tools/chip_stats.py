@@ -218,6 +218,30 @@ class Walker:
         return n_c, inter
 
 
+def ref_gkr_workloads():
+    """reference-held cross-check: sp1-gpu/crates/logup_gkr/layer_workloads.json records, for 119 real shards, the row count of every
+    (chip, interaction) pair.  Runs of equal row counts = the interactions of one chip."""
+    import itertools
+    import statistics
+    p = "/root/reference/sp1-gpu/crates/logup_gkr/layer_workloads.json"
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    per_chip, totals, n_inter = [], [], []
+    for x in d:
+        rc = x["interaction_row_counts"]
+        totals.append(sum(rc)); n_inter.append(len(rc))
+        for h, g in itertools.groupby(rc):
+            n = len(list(g))
+            if h > 2:
+                per_chip.append(n)
+    q = sorted(per_chip)
+    return {"source": "sp1-gpu/crates/logup_gkr/layer_workloads.json", "shards": len(d),
+            "interactions_per_chip": {"median": statistics.median(q), "mean": round(statistics.mean(q), 1), "p10": q[len(q) // 10], "p90": q[9 * len(q) // 10]},
+            "interactions_per_shard": {"median": statistics.median(n_inter), "min": min(n_inter), "max": max(n_inter)},
+            "sum_rows_times_interactions": {"median": statistics.median(totals), "max": max(totals)}}
+
+
 def main():
     idx = Index()
     w = Walker(idx)
@@ -239,7 +263,8 @@ def main():
                      "mean_values": round(sum(inter) / max(1, len(inter)), 2), "source": f"{tgt[2]}:{tgt[3]}"}
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sp1_b200", "chip_stats.json")
     meta = {"generator": "tools/chip_stats.py (static reading of the reference's Rust eval functions; heuristic, see the script header)",
-            "reference": "succinctlabs/sp1 v6.4.0, crates/core/machine/src", "chips": out}
+            "reference": "succinctlabs/sp1 v6.4.0, crates/core/machine/src", "chips": out,
+            "reference_gkr_workloads": ref_gkr_workloads()}
     json.dump(meta, open(path, "w"), indent=1)
     for k, v in out.items():
         print(f"{k:22s}", v if "error" in v else (v["constraints"], v["interactions"], v["mean_values"], v["source"]))

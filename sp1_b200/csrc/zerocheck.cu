@@ -57,8 +57,10 @@ template <> struct Ops<Ext> {
 struct ZcJob {
     const void* main; const void* prep; const uint32_t* alpha_pows; uint64_t h;
     uint32_t blk_start, nblk, chip, columns;   // columns != 0: this job also evaluates the opening-batching term
-    uint32_t zc_begin, zc_end, pad0, pad1;     // the piece of the chip's instruction stream this job interprets
+    uint32_t zc_begin, zc_end;                 // the piece of the chip's instruction stream this job interprets
+    const void* batch;                         // EF rounds: the chip's pre-batched column B[r] = sum_j gamma^(j+1) col_j[r] (nullptr in round 0)
 };
+static_assert(sizeof(ZcJob) == 64, "ZcJob layout");
 struct ZcFixJob {
     const void* main; const void* prep; uint32_t* out; uint64_t h;
     uint32_t main_w, prep_w, blk_start, pad;
@@ -204,6 +206,14 @@ __global__ void __launch_bounds__(ZC_BLOCK) zc_sum_kernel(const ZcJob* __restric
         // the opening-batching term is linear in the row variable: evaluate it at 0 and 1 only
         Ext s0 = kb::ext_zero(), s1 = kb::ext_zero();
         const bool has_o = 2 * i + 1 < h;
+        if (job.batch) {
+            // EF rounds: the term is linear in the columns too, so it is carried as ONE pre-batched column per chip that is folded
+            // with the others (zc_batch0_kernel builds it after round 0): two loads instead of 2 x width extension products
+            const uint32_t* B = static_cast<const uint32_t*>(job.batch);
+            acc[3] = kb::ext_add(acc[3], kb::ext_mul(kb::ext_load(B + 8 * i), e));
+            if (has_o) acc[4] = kb::ext_add(acc[4], kb::ext_mul(kb::ext_load(B + 8 * i + 4), e));
+            continue;
+        }
         for (uint32_t j = 0; j < prog.main_w; j++) {
             const Ext g = kb::ext_load(gkr_pows + 4 * j);
             const K* c = main + (uint64_t)j * h;
@@ -281,6 +291,28 @@ __global__ void __launch_bounds__(256) zc_fix_kernel(const ZcFixJob* __restrict_
     if constexpr (sizeof(K) == 4) r = kb::ext_add(kb::ext_from_base(a), kb::ext_mul_base(alpha, kb::sub(b, a)));
     else r = kb::ext_add(a, kb::ext_mul(alpha, kb::ext_sub(b, a)));
     kb::ext_store(job.out + 4 * t, r);
+}
+
+// After round 0: the pre-batched column of every chip in the first EF arena,
+//   B[i] = sum_j g_j (col_j[2i] + alpha (col_j[2i+1] - col_j[2i])) = sum_j g_j a_j + alpha sum_j g_j (b_j - a_j)      (base-field a, b)
+// one thread per output row, EF x F products only.  job.out = the chip's B column; job.main / job.prep = the BASE columns.
+__global__ void __launch_bounds__(256) zc_batch0_kernel(const ZcFixJob* __restrict__ jobs, int n_jobs, const uint32_t* __restrict__ gkr_pows, Ext alpha) {
+    const ZcFixJob job = jobs[find_job(jobs, n_jobs, blockIdx.x)];
+    const uint64_t h = job.h, nh = (h + 1) / 2;
+    const uint64_t i = (uint64_t)(blockIdx.x - job.blk_start) * 256 + threadIdx.x;
+    if (i >= nh) return;
+    const bool has_o = 2 * i + 1 < h;
+    Ext sa = kb::ext_zero(), sd = kb::ext_zero();
+    const uint32_t* main = static_cast<const uint32_t*>(job.main);
+    const uint32_t* prep = static_cast<const uint32_t*>(job.prep);
+    for (uint32_t j = 0; j < job.main_w + job.prep_w; j++) {
+        const uint32_t* c = j < job.main_w ? main + (uint64_t)j * h : prep + (uint64_t)(j - job.main_w) * h;
+        const uint32_t a = __ldg(c + 2 * i), b = has_o ? __ldg(c + 2 * i + 1) : 0u;
+        const Ext g = kb::ext_load(gkr_pows + 4 * j);
+        sa = kb::ext_add(sa, kb::ext_mul_base(g, a));
+        sd = kb::ext_add(sd, kb::ext_mul_base(g, kb::sub(b, a)));
+    }
+    kb::ext_store(job.out + 4 * i, kb::ext_add(sa, kb::ext_mul(alpha, sd)));
 }
 
 __global__ void zc_eq_table_kernel(const uint32_t* __restrict__ point, int k, uint32_t* __restrict__ E) {
@@ -509,8 +541,8 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
         s.vg.threshold = (uint32_t)s.h; s.vg.geq_c = E4::one();
         const uint64_t nh = (s.h + 1) / 2;
         const size_t w = p.main_w + p.prep_w;
-        boff0[k] = b0; b0 += (uint64_t)w * nh * 4;
-        boff1[k] = b1; b1 += (uint64_t)w * ((nh + 1) / 2) * 4;
+        boff0[k] = b0; b0 += (uint64_t)(w + 1) * nh * 4;               // + the pre-batched opening column B (zc_batch0_kernel)
+        boff1[k] = b1; b1 += (uint64_t)(w + 1) * ((nh + 1) / 2) * 4;
         woff[k] = wsum; wsum += w;
     }
     SP1_TRY(mem.alloc((void**)&d_ap, all_ap.size() * 16));
@@ -537,7 +569,8 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
     struct RoundPlan { std::vector<Launch> sums; size_t fix0; uint32_t fix_jobs, fix_blocks; std::vector<uint32_t> chip_of_job; size_t job0; };
     std::vector<RoundPlan> plan(mlr);
     std::vector<ZcJob> jobs;
-    std::vector<ZcFixJob> fjobs;
+    std::vector<ZcFixJob> fjobs, bjobs;      // bjobs: zc_batch0_kernel (after round 0)
+    uint32_t batch_blocks = 0;
     const unsigned MAXB = 148 * 4;
     uint32_t max_blocks = 1, max_jobs = 1;
     {
@@ -552,9 +585,14 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
             };
             auto in_prep = [&](size_t k) -> const void* {
                 const ChipProg& p = m->chips[k];
-                if (!p.prep_w) return nullptr;
-                if (rd == 0) return d_prep[k];
+                if (rd == 0) return p.prep_w ? d_prep[k] : nullptr;
+                // EF arenas: main columns, preprocessed columns, then B - contiguous (also when the chip has no preprocessed column)
                 return static_cast<const uint32_t*>(in_main(k)) + (uint64_t)p.main_w * hcur[k] * 4;
+            };
+            auto in_batch = [&](size_t k) -> const void* {
+                if (rd == 0) return nullptr;
+                const ChipProg& p = m->chips[k];
+                return static_cast<const uint32_t*>(in_main(k)) + (uint64_t)(p.main_w + p.prep_w) * hcur[k] * 4;
             };
             uint32_t blocks_round = 0;
             for (int tier = 0; tier < 5; tier++) {
@@ -571,13 +609,13 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
                     if (nb <= 16 && !pieces.empty()) {
                         for (size_t q = 0; q < pieces.size(); q++) {
                             ZcJob j{in_main(k), in_prep(k), d_ap + 4 * ap_off[k], hcur[k], Lc.blocks, nb, (uint32_t)k, q == 0 ? 1u : 0u,
-                                    pieces[q].first, pieces[q].first + pieces[q].second, 0, 0};
+                                    pieces[q].first, pieces[q].first + pieces[q].second, in_batch(k)};
                             jobs.push_back(j);
                             R.chip_of_job.push_back((uint32_t)k);
                             Lc.n_jobs++; Lc.blocks += nb;
                         }
                     } else {
-                        ZcJob j{in_main(k), in_prep(k), d_ap + 4 * ap_off[k], hcur[k], Lc.blocks, nb, (uint32_t)k, 1u, 0u, p.n_zc, 0, 0};
+                        ZcJob j{in_main(k), in_prep(k), d_ap + 4 * ap_off[k], hcur[k], Lc.blocks, nb, (uint32_t)k, 1u, 0u, p.n_zc, in_batch(k)};
                         jobs.push_back(j);
                         R.chip_of_job.push_back((uint32_t)k);
                         Lc.n_jobs++; Lc.blocks += nb;
@@ -597,16 +635,27 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
                 if (!hcur[k]) continue;
                 const uint64_t nh = (hcur[k] + 1) / 2;
                 uint32_t* out = rd + 1 == mlr ? d_final + 4 * woff[k] : (rd & 1 ? d_buf[1] + boff1[k] : d_buf[0] + boff0[k]);
-                ZcFixJob f{in_main(k), in_prep(k), out, hcur[k], p.main_w, p.prep_w, R.fix_blocks, 0};
+                // EF rounds fold the pre-batched column B along with the chip's columns (it sits right after the preprocessed columns, so
+                // it is simply one more "preprocessed" column of the fix job); the last round's output is the opened values only
+                const uint32_t fold_b = (rd > 0 && rd + 1 < mlr) ? 1u : 0u;
+                ZcFixJob f{in_main(k), in_prep(k), out, hcur[k], p.main_w, p.prep_w + fold_b, R.fix_blocks, 0};
                 fjobs.push_back(f);
-                R.fix_jobs++; R.fix_blocks += blocks_for(nh, 256) * (p.main_w + p.prep_w);   // one column per block row (zc_fix_kernel)
+                R.fix_jobs++; R.fix_blocks += blocks_for(nh, 256) * (p.main_w + p.prep_w + fold_b);   // one column per block row (zc_fix_kernel)
+                if (rd == 0 && mlr > 1) {   // B of the first EF round, from the base columns
+                    ZcFixJob bj{d_main[k], m->chips[k].prep_w ? d_prep[k] : nullptr, d_buf[0] + boff0[k] + (uint64_t)(p.main_w + p.prep_w) * nh * 4, hcur[k],
+                                p.main_w, p.prep_w, batch_blocks, 0};
+                    bjobs.push_back(bj);
+                    batch_blocks += blocks_for(nh, 256);
+                }
                 hcur[k] = nh;
             }
         }
     }
-    ZcJob* d_jobs; ZcFixJob* d_fjobs; uint32_t *d_partial, *d_sums;
+    ZcJob* d_jobs; ZcFixJob *d_fjobs, *d_bjobs; uint32_t *d_partial, *d_sums;
     SP1_TRY(mem.alloc((void**)&d_jobs, (jobs.size() + 1) * sizeof(ZcJob)));
     SP1_TRY(mem.alloc((void**)&d_fjobs, (fjobs.size() + 1) * sizeof(ZcFixJob)));
+    SP1_TRY(mem.alloc((void**)&d_bjobs, (bjobs.size() + 1) * sizeof(ZcFixJob)));
+    if (!bjobs.empty()) SP1_CUDA(cudaMemcpyAsync(d_bjobs, bjobs.data(), bjobs.size() * sizeof(ZcFixJob), cudaMemcpyHostToDevice, st));
     if (!jobs.empty()) SP1_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(ZcJob), cudaMemcpyHostToDevice, st));
     if (!fjobs.empty()) SP1_CUDA(cudaMemcpyAsync(d_fjobs, fjobs.data(), fjobs.size() * sizeof(ZcFixJob), cudaMemcpyHostToDevice, st));
     SP1_TRY(mem.alloc((void**)&d_partial, (size_t)max_blocks * 36 * 4));
@@ -710,8 +759,10 @@ sp1b200_err sp1b200_zerocheck(sp1b200_ctx* ctx, const sp1b200_machine* m, const 
         point.insert(point.begin(), a);
         const Ext da{{a.c[0], a.c[1], a.c[2], a.c[3]}};
         if (R.fix_jobs) {
-            if (rd == 0) SP1_LAUNCH(ctx, zc_fix_kernel<uint32_t>, R.fix_blocks, 256, 0, d_fjobs + R.fix0, (int)R.fix_jobs, da);
-            else SP1_LAUNCH(ctx, zc_fix_kernel<Ext>, R.fix_blocks, 256, 0, d_fjobs + R.fix0, (int)R.fix_jobs, da);
+            if (rd == 0) {
+                SP1_LAUNCH(ctx, zc_fix_kernel<uint32_t>, R.fix_blocks, 256, 0, d_fjobs + R.fix0, (int)R.fix_jobs, da);
+                if (!bjobs.empty()) SP1_LAUNCH(ctx, zc_batch0_kernel, batch_blocks, 256, 0, d_bjobs, (int)bjobs.size(), d_gw, da);
+            } else SP1_LAUNCH(ctx, zc_fix_kernel<Ext>, R.fix_blocks, 256, 0, d_fjobs + R.fix0, (int)R.fix_jobs, da);
         }
         E4 La[4];  // L_i(a) for the four non-zero nodes
         for (int i = 0; i < 4; i++) La[i] = hf::eval_poly<5>(basis[i], a);

@@ -28,6 +28,19 @@ def test_library_exports_every_declared_symbol():
     assert set(syms) == known, (set(syms) ^ known)
 
 
+def test_library_exports_only_the_c_abi():
+    """nothing but the C ABI leaves the product library: no C++ helpers, no test hooks (the host-compiled device arithmetic used by
+    the CPU suite lives in its own libsp1b200_hostcheck.so)"""
+    import subprocess
+    from sp1_b200 import lib as B
+    out = subprocess.run(["nm", "-D", "--defined-only", B.SO_PATH], capture_output=True, text=True, check=True).stdout
+    exported = [l.split()[-1] for l in out.splitlines() if len(l.split()) == 3 and l.split()[1] in "TtDB"]
+    assert exported and all(n.startswith("sp1b200_") for n in exported), [n for n in exported if not n.startswith("sp1b200_")]
+    assert not [n for n in exported if "hostcheck" in n]
+    internal = {"sp1b200_mail_wait", "sp1b200_upload_acquire", "sp1b200_upload_release"}   # extern "C" helpers shared between the library's own TUs
+    assert set(exported) - internal == set(_declared_symbols())
+
+
 def test_version_string():
     from sp1_b200 import lib as B
     assert b"sm_100a" in B.load().sp1b200_version()

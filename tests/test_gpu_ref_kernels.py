@@ -35,7 +35,8 @@ def test_field_ops_reference_vs_oracle_vs_product():
     n = 4096
     a, b = _edge_field(rng, n), _edge_field(rng, n)[::-1].copy()
     L = O.lib()
-    P = __import__("sp1_b200").load()
+    from tests import hostcheck_lib
+    P = hostcheck_lib.load()
     for op, f in (("add", L.orc_add), ("sub", L.orc_sub), ("mul", L.orc_mul)):
         ref = R.field_op(op, a, b)
         exp = np.array([f(int(x), int(y)) for x, y in zip(a, b)], np.uint32)
@@ -56,7 +57,8 @@ def test_ext_ops_reference_vs_oracle_vs_product():
     a, b = O.rand_field(rng, (n, 4)), O.rand_field(rng, (n, 4))
     a[0] = 0; a[1] = [0x01FFFFFE, 0, 0, 0]; b[2] = 0; a[3] = O.to_monty(np.full(4, O.P - 1))
     L = O.lib()
-    P = __import__("sp1_b200").load()
+    from tests import hostcheck_lib
+    P = hostcheck_lib.load()
     ref_mul = R.ext_op("mul", a, b)
     exp = np.zeros_like(a)
     for i in range(n):

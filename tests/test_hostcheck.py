@@ -8,8 +8,8 @@ from tests import oracle_lib as O
 
 
 def _L():
-    from sp1_b200 import lib as B
-    return B.load()
+    from tests import hostcheck_lib as H
+    return H.load()
 
 
 def _edge_states(rng, n):

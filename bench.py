@@ -330,6 +330,18 @@ def run_queue(args):
         provers.append((l_, m_, p_))
     chal0 = HostChallenger().st.copy()
     names = base["names"]
+    # the job moves every shard's trace over PCIe: measure this rank's host->device bandwidth (pinned, 256 MiB, best of 3) so that the
+    # limiter can be named from the same run
+    probe_h = torch.empty(64 << 20, dtype=torch.int32, pin_memory=True)
+    probe_d = torch.empty(64 << 20, dtype=torch.int32, device=dev)
+    h2d_gbs = 0.0
+    for _ in range(3):
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record(); probe_d.copy_(probe_h, non_blocking=True); b_.record(); torch.cuda.synchronize()
+        h2d_gbs = max(h2d_gbs, probe_h.numel() * 4 / (a_.elapsed_time(b_) / 1e3) / 1e9)
+    del probe_h, probe_d
+    h2d_min = -SH.max_over_ranks(-h2d_gbs, dev)
+    h2d_max = SH.max_over_ranks(h2d_gbs, dev)
 
     def worker(who, q, proofs, busy):
         l_, m_, p_ = provers[who]
@@ -399,8 +411,12 @@ def run_queue(args):
                           "how": "all_gather of the (index, length) table + one NCCL gather of padded words; rank 0 enters the collective when ITS "
                                  "shards are done, so this time includes waiting for the slowest rank"},
                "rank0_context_busy_s": [round(b, 3) for b in busy], "gpu_launches": int(launches), "clocks": clocks,
-               "limiter": "per-shard proving time; the queue is static across ranks (round-robin), so the slowest rank (most cells) sets the time; "
-                          "the gather is a few ms"}
+               "h2d_probe_gb_per_s": {"min_over_ranks": h2d_min, "max_over_ranks": h2d_max, "how": "pinned 256 MiB host->device copy, best of 3, per rank"},
+               "bytes_per_shard": int(h_traces[variants[0]].numel() * 4),
+               "limiter": "host->device trace transfer: a full shard is %.2f GB and is proven in ~0.12 s, i.e. %.1f GB/s per GPU are needed to keep the "
+                          "provers busy while the measured pinned H2D rate is %.1f-%.1f GB/s per GPU (shared host); then the static round-robin placement "
+                          "(8 shards over 3 contexts per rank = 3 waves) and the wait for the slowest rank inside the gather"
+                          % (h_traces[variants[0]].numel() * 4 / 1e9, h_traces[variants[0]].numel() * 4 / 1e9 / 0.124, h2d_min, h2d_max)}
         print(json.dumps(out))
     for l_, m_, p_ in provers:
         l_.jagged_round_free(p_); l_.machine_free(m_); l_.close()

@@ -108,3 +108,33 @@ def test_context_rejects_a_missing_device():
     from sp1_b200.lib import Sp1B200Error
     with pytest.raises(Sp1B200Error, match="not present"):
         Lib(device=64)
+
+
+def test_repeated_contexts_and_proofs_do_not_leak_device_memory():
+    """create / prove / destroy in a loop: device memory in use returns to its starting level (contexts own their pools, slots,
+    mailboxes; failure paths of ctx_create and jagged_commit release what they allocated)"""
+    import torch
+    from sp1_b200 import Lib
+    rng = np.random.default_rng(4)
+    blob, heights, mains, preps, pv = _machine(rng)
+    names = [f"Chip{i:02d}" for i in range(len(heights))]
+    dense = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(m).reshape(-1) for m in mains if m.size]))
+    torch.cuda.synchronize()
+    used = []
+    ref = None
+    for it in range(6):
+        L = Lib(0, log_stacking_height=10, max_log_row_count=11, num_queries=8, pow_bits=4, batch_pow_bits=2, gkr_pow_bits=3)
+        mach = L.machine_create(blob)
+        _, prep_round = L.jagged_commit([p for p in preps if p is not None])
+        for _ in range(3):
+            w = L.prove_shard(mach, prep_round, dense, heights, names, pv, O.Challenger().st.copy())
+            if ref is None:
+                ref = w
+            assert (w == ref).all()
+        L.jagged_round_free(prep_round)
+        L.machine_free(mach)
+        L.close()
+        torch.cuda.synchronize()
+        free, total = torch.cuda.mem_get_info(0)
+        used.append(total - free)
+    assert max(used[1:]) - min(used[1:]) < (64 << 20), used     # steady after the first iteration (CUDA context / module loading)

@@ -413,10 +413,10 @@ def run_queue(args):
                "rank0_context_busy_s": [round(b, 3) for b in busy], "gpu_launches": int(launches), "clocks": clocks,
                "h2d_probe_gb_per_s": {"min_over_ranks": h2d_min, "max_over_ranks": h2d_max, "how": "pinned 256 MiB host->device copy, best of 3, per rank"},
                "bytes_per_shard": int(h_traces[variants[0]].numel() * 4),
-               "limiter": "host->device trace transfer: a full shard is %.2f GB and is proven in ~0.12 s, i.e. %.1f GB/s per GPU are needed to keep the "
-                          "provers busy while the measured pinned H2D rate is %.1f-%.1f GB/s per GPU (shared host); then the static round-robin placement "
-                          "(8 shards over 3 contexts per rank = 3 waves) and the wait for the slowest rank inside the gather"
-                          % (h_traces[variants[0]].numel() * 4 / 1e9, h_traces[variants[0]].numel() * 4 / 1e9 / 0.124, h2d_min, h2d_max)}
+               "limiter": "static placement: %d shards per rank over %d contexts = %d waves (the last one partly empty), plus rank 0 waiting inside the gather "
+                          "for the slowest rank; the traces need %.1f GB/s of H2D per GPU to keep the provers busy and the measured pinned rate is "
+                          "%.1f-%.1f GB/s per GPU, so the transfer is hidden behind the proofs"
+                          % (len(mine), len(provers), -(-len(mine) // len(provers)), h_traces[variants[0]].numel() * 4 / 1e9 / 0.124, h2d_min, h2d_max)}
         print(json.dumps(out))
     for l_, m_, p_ in provers:
         l_.jagged_round_free(p_); l_.machine_free(m_); l_.close()

@@ -192,9 +192,9 @@ def run_reference(args):
 
 
 def default_inflight(args):
-    """shards proven concurrently per GPU: as many as the device memory comfortably holds (measured: ~17-24 GB per S2 context at the
-    pool's high water mark; throughput saturates at 5-6 contexts), never more than 5"""
-    return args.inflight if args.inflight > 0 else {"S1": 5, "S2": 5, "S1c": 5, "S2c": 5, "R1": 5, "tiny": 4, "tinyc": 4, "tinyr": 4}.get(args.workload, 3)
+    """shards proven concurrently per GPU: as many as the device memory comfortably holds (measured: 13.7 GB per calibrated 2^22-cycle
+    context, 26-32 GB per full shard; throughput saturates at 5 / 4 contexts: S3c 73.4 M cycles/s at three, 78.1 M at four in flight)"""
+    return args.inflight if args.inflight > 0 else {"S1": 5, "S2": 5, "S1c": 5, "S2c": 5, "R1": 5, "tiny": 4, "tinyc": 4, "tinyr": 4}.get(args.workload, 4)
 
 
 def workload_config(workload, cells, cycles, n_chips, inflight):

@@ -259,6 +259,26 @@ sp1b200_err sp1b200_setup_and_prove_shard(sp1b200_ctx* ctx, const sp1b200_machin
                                           sp1b200_jagged_round** prep_round_out, uint32_t* h_proof, uint64_t proof_cap_words,
                                           uint64_t* h_proof_words);
 
+/* ---- ShardProof wire format ----------------------------------------------------------------------------------------
+ * The reference moves shard proofs between prover workers, the recursion tree and the verifier as bincode(ShardProof)
+ * (crates/hypercube/src/verifier/proof.rs:47-61 and the nested types listed in csrc/wire.cu; bincode 1.3 default configuration:
+ * little endian, fixed-width integers, u64 lengths, Option tag u8).  Field elements travel as CANONICAL u32 words (pinned by the
+ * reference-held crates/prover/src/vk_map_dummy.bin, tests/golden/bincode_pins.json), extension elements as 4 of them, chip maps in
+ * name order with the names as strings, chip heights as the `degree` bit points.  Host-only calls: no context, no device work.
+ * n_chips / chip_names (strictly ascending) / h_main_w / h_prep_w describe the shard's chips (the machine passed to sp1b200_prove_shard). */
+
+/* flat words of sp1b200_prove_shard -> bincode(ShardProof).  h_out may be NULL to query *h_out_bytes. */
+sp1b200_err sp1b200_shard_proof_to_bincode(const sp1b200_params* params, uint32_t n_chips, const char* const* chip_names,
+                                           const uint64_t* h_heights, const uint32_t* h_main_w, const uint32_t* h_prep_w,
+                                           const uint32_t* h_proof, uint64_t n_words, uint8_t* h_out, uint64_t cap_bytes,
+                                           uint64_t* h_out_bytes);
+/* bincode(ShardProof) -> flat words; every length prefix, tensor dimension, chip name / width and the canonical range of every field
+ * element is checked.  h_heights_out (n_chips, optional) receives the heights decoded from the degree points; h_proof may be NULL to
+ * query *h_words. */
+sp1b200_err sp1b200_shard_proof_from_bincode(const sp1b200_params* params, uint32_t n_chips, const char* const* chip_names,
+                                             const uint32_t* h_main_w, const uint32_t* h_prep_w, const uint8_t* h_bytes, uint64_t n_bytes,
+                                             uint64_t* h_heights_out, uint32_t* h_proof, uint64_t cap_words, uint64_t* h_words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,7 +58,7 @@ ERR_FUNCS = [
     "sp1b200_memcpy_d2h", "sp1b200_upload_begin", "sp1b200_pack_row_major", "sp1b200_poseidon2_permute", "sp1b200_rs_encode", "sp1b200_merkle_commit", "sp1b200_grind",
     "sp1b200_stacked_commit", "sp1b200_stacked_prove", "sp1b200_jagged_commit", "sp1b200_jagged_column_claims",
     "sp1b200_jagged_prove", "sp1b200_machine_create", "sp1b200_zerocheck", "sp1b200_logup_gkr", "sp1b200_prove_shard",
-    "sp1b200_setup_and_prove_shard",
+    "sp1b200_setup_and_prove_shard", "sp1b200_shard_proof_to_bincode", "sp1b200_shard_proof_from_bincode",
 ]
 OTHER_FUNCS = ["sp1b200_challenger_init", "sp1b200_challenger_observe", "sp1b200_challenger_sample",
                "sp1b200_challenger_sample_bits", "sp1b200_challenger_check_witness", "sp1b200_ctx_destroy", "sp1b200_default_core_params", "sp1b200_version", "sp1b200_ctx_stream",
@@ -329,3 +329,49 @@ class HostChallenger:
 
     def check_witness(self, bits, w):
         return bool(self.L.sp1b200_challenger_check_witness(_ptr(self.st), C.c_uint32(bits), C.c_uint32(w)))
+
+
+# ---- ShardProof wire format (host only, no context): flat proof words <-> bincode(ShardProof) ---------------------------------------
+def _wire_args(params, names, main_w, prep_w):
+    p = dict(DEFAULT_CORE_PARAMS)
+    p.update(params)
+    n = len(names)
+    return (Params(**p), C.c_uint32(n), (C.c_char_p * n)(*[s.encode() for s in names]), (C.c_uint32 * n)(*[int(x) for x in main_w]),
+            (C.c_uint32 * n)(*[int(x) for x in prep_w]))
+
+
+def shard_proof_to_bincode(words, names, heights, main_w, prep_w, **params):
+    """flat words of prove_shard -> bytes of bincode(ShardProof) (crates/hypercube/src/verifier/proof.rs:47-61)"""
+    L = load()
+    P, n, NM, MW, PW = _wire_args(params, names, main_w, prep_w)
+    H = (C.c_uint64 * len(names))(*[int(h) for h in heights])
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    nb = C.c_uint64()
+    err = L.sp1b200_shard_proof_to_bincode(C.byref(P), n, NM, H, MW, PW, _ptr(w), C.c_uint64(w.size), None, C.c_uint64(0), C.byref(nb))
+    if err:
+        raise Sp1B200Error(err.decode())
+    out = np.empty(nb.value, np.uint8)
+    err = L.sp1b200_shard_proof_to_bincode(C.byref(P), n, NM, H, MW, PW, _ptr(w), C.c_uint64(w.size), C.c_void_p(out.ctypes.data),
+                                           C.c_uint64(out.size), C.byref(nb))
+    if err:
+        raise Sp1B200Error(err.decode())
+    return out.tobytes()
+
+
+def shard_proof_from_bincode(data, names, main_w, prep_w, **params):
+    """bytes of bincode(ShardProof) -> (flat words, chip heights)"""
+    L = load()
+    P, n, NM, MW, PW = _wire_args(params, names, main_w, prep_w)
+    buf = np.frombuffer(bytes(data), np.uint8)
+    H = (C.c_uint64 * max(1, len(names)))()
+    nw = C.c_uint64()
+    err = L.sp1b200_shard_proof_from_bincode(C.byref(P), n, NM, MW, PW, C.c_void_p(buf.ctypes.data), C.c_uint64(buf.size), H, None,
+                                             C.c_uint64(0), C.byref(nw))
+    if err:
+        raise Sp1B200Error(err.decode())
+    out = np.empty(nw.value, np.uint32)
+    err = L.sp1b200_shard_proof_from_bincode(C.byref(P), n, NM, MW, PW, C.c_void_p(buf.ctypes.data), C.c_uint64(buf.size), H, _ptr(out),
+                                             C.c_uint64(out.size), C.byref(nw))
+    if err:
+        raise Sp1B200Error(err.decode())
+    return out, [int(H[i]) for i in range(len(names))]

@@ -16,6 +16,23 @@ void sp1b200_hostcheck_permute(uint32_t* states, uint64_t n) {
         for (int k = 0; k < 16; k++) states[i * 16 + k] = s[k];
     }
 }
+// every instruction-selection mode of the permutation (poseidon2.cuh, permute_m<MODE>); returns 0 for an unknown mode
+int sp1b200_hostcheck_permute_mode(uint32_t* states, uint64_t n, int mode) {
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t s[16];
+        for (int k = 0; k < 16; k++) s[k] = states[i * 16 + k];
+        switch (mode) {
+#define P2_CASE(M) case M: p2::permute_m<M>(s); break;
+            P2_CASE(0) P2_CASE(1) P2_CASE(2) P2_CASE(3) P2_CASE(4) P2_CASE(5) P2_CASE(6) P2_CASE(7)
+            P2_CASE(8) P2_CASE(9) P2_CASE(10) P2_CASE(11) P2_CASE(12) P2_CASE(13) P2_CASE(14) P2_CASE(15)
+#undef P2_CASE
+            case -1: p2::permute_r1(s); break;
+            default: return 0;
+        }
+        for (int k = 0; k < 16; k++) states[i * 16 + k] = s[k];
+    }
+    return 1;
+}
 void sp1b200_hostcheck_ext_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, uint64_t n) {
     for (uint64_t i = 0; i < n; i++) {
         kb::Ext x{{a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]}}, y{{b[4 * i], b[4 * i + 1], b[4 * i + 2], b[4 * i + 3]}};

@@ -131,7 +131,7 @@ KB_HD void int_layer_lazy(uint32_t (&s)[16]) {
 
 // Loop shapes measured with tools/p2_bench.cu on a B200: full rounds unrolled x2 and partial rounds x4 give 4.61 Gperm/s,
 // rolled loops 4.50, fully unrolled code 4.01 (instruction cache).
-KB_HD void permute(uint32_t (&s)[16]) {
+KB_HD void permute_r1(uint32_t (&s)[16]) {
     ext_layer(s);
 #pragma unroll 2
     for (int r = 0; r < 4; r++) {
@@ -153,6 +153,128 @@ KB_HD void permute(uint32_t (&s)[16]) {
         for (int i = 0; i < 16; i++) s[i] = sbox(s[i], P2_RC.ext[r * 16 + i]);
         ext_layer(s);
     }
+}
+
+// ---- pipe-aware permutation (round 2) ---------------------------------------------------------------------------------------------
+// ncu on the leaf-hash kernel (profiles/ncu_leaf_hash_r01.txt): issue-active 63 %, alu pipe 51 %, top stall math_pipe_throttle - the
+// multiplier side of the fma pipe is the limiter, and ptxas puts a large share of the plain additions (IMAD.IADD), negations (IMAD.MOV)
+// and carries (IMAD.X) on that same pipe.  permute_m<MODE> is the same permutation with the instruction selection steered:
+//   M_SB_SUB   s-box products reduced in the subtractive Montgomery form  hi(t) - hi(lo(t) p^-1 p)  (IMAD.WIDE, IMAD, IMAD.HI, IADD3):
+//              the additive form (mad.wide with a 64-bit addend) is expanded by ptxas into IMAD.HI + negate + carry + IMAD.X, two more
+//              instructions per product, most of them on the fma pipe                     (5456 -> 4864 instructions per permutation)
+//   M_EXT_ALU  the 68 modular additions of every external linear layer issue their first add as VIADDMNMX(a + b, 0xffffffff) - alu pipe
+//              by construction (the all-ones operand comes from constant memory, so the compiler cannot fold the min away)
+//   M_INT_ALU  same for the subtractions  t - q  of the internal layer (VIADDMNMX with a negated operand)
+//   M_SB_HALF  s-box products by halves (IMAD + IMAD.HI) instead of IMAD.WIDE
+// tools/p2_bench.cu times the combinations (profiles/p2_bench_r02b.txt); P2_DEFAULT_MODE is the measured best.  Every mode computes the
+// same words: tests/test_hostcheck.py runs them on the host against the oracle, tools/p2_bench.cu and the GPU suite on the device.
+enum : int { M_SB_SUB = 1, M_EXT_ALU = 2, M_INT_ALU = 4, M_SB_HALF = 8 };
+#ifndef P2_DEFAULT_MODE
+#define P2_DEFAULT_MODE 0
+#endif
+static __constant__ uint32_t K_ONES = 0xffffffffu;
+
+template <bool ALU> KB_HD uint32_t addw(uint32_t a, uint32_t b) {   // a + b mod 2^32
+#ifdef __CUDA_ARCH__
+    if (ALU) return __viaddmin_u32(a, b, K_ONES);
+#endif
+    return a + b;
+}
+template <bool ALU> KB_HD uint32_t subw(uint32_t a, uint32_t b) {   // a - b mod 2^32
+#ifdef __CUDA_ARCH__
+    if (ALU) return __viaddmin_u32(a, 0u - b, K_ONES);
+#endif
+    return a - b;
+}
+template <bool ALU> KB_HD uint32_t add_m(uint32_t a, uint32_t b) { const uint32_t t = addw<ALU>(a, b); return umin(t, t - kb::P); }
+
+template <bool ALU> KB_HD void mds4_m(uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
+    uint32_t t01 = add_m<ALU>(s0, s1), t23 = add_m<ALU>(s2, s3);
+    uint32_t t0123 = add_m<ALU>(t01, t23);
+    uint32_t t01123 = add_m<ALU>(t0123, s1);
+    uint32_t t01233 = add_m<ALU>(t0123, s3);
+    uint32_t n3 = add_m<ALU>(t01233, add_m<ALU>(s0, s0));
+    uint32_t n1 = add_m<ALU>(t01123, add_m<ALU>(s2, s2));
+    uint32_t n0 = add_m<ALU>(t01123, t01);
+    uint32_t n2 = add_m<ALU>(t01233, t23);
+    s0 = n0; s1 = n1; s2 = n2; s3 = n3;
+}
+template <bool ALU> KB_HD void ext_layer_m(uint32_t (&s)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) mds4_m<ALU>(s[i], s[i + 1], s[i + 2], s[i + 3]);
+    uint32_t c0 = add_m<ALU>(add_m<ALU>(s[0], s[4]), add_m<ALU>(s[8], s[12]));
+    uint32_t c1 = add_m<ALU>(add_m<ALU>(s[1], s[5]), add_m<ALU>(s[9], s[13]));
+    uint32_t c2 = add_m<ALU>(add_m<ALU>(s[2], s[6]), add_m<ALU>(s[10], s[14]));
+    uint32_t c3 = add_m<ALU>(add_m<ALU>(s[3], s[7]), add_m<ALU>(s[11], s[15]));
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+        s[i] = add_m<ALU>(s[i], c0); s[i + 1] = add_m<ALU>(s[i + 1], c1); s[i + 2] = add_m<ALU>(s[i + 2], c2); s[i + 3] = add_m<ALU>(s[i + 3], c3);
+    }
+}
+
+// a*b*2^-32 + off, subtractive form: exact difference in (-p, p) + off for a*b < 2^32 p
+template <bool HALF> KB_HD uint32_t mont_sub(uint32_t a, uint32_t b, uint32_t off) {
+    uint32_t lo, hi;
+    if (HALF) { lo = a * b; hi = kb::mulhi(a, b); }
+    else { const uint64_t t = (uint64_t)a * b; lo = (uint32_t)t; hi = (uint32_t)(t >> 32); }
+    return hi - kb::mulhi(lo * MU, kb::P) + off;
+}
+template <int MODE> KB_HD uint32_t sbox_m(uint32_t s, uint32_t rc) {
+    if (!(MODE & M_SB_SUB)) return sbox(s, rc);
+    const uint32_t x = kb::add(s, rc);
+    const uint32_t x2 = mont_sub<(MODE & M_SB_HALF) != 0>(x, x, kb::P);   // (0, 2p)
+    const uint32_t r = mont_sub<(MODE & M_SB_HALF) != 0>(x2, x, 0);       // x2 x < 2 p^2 < 2^32 p ; (-p, p)
+    return umin(r, r + kb::P);
+}
+
+template <bool ALU> KB_HD void int_layer_m(uint32_t (&s)[16]) {   // int_layer_lazy with the subtractions placed on the alu pipe
+    uint64_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) sum += s[i];
+    const uint32_t slo = (uint32_t)sum, shi = (uint32_t)(sum >> 32);
+    const uint32_t r = subw<ALU>(shi, kb::mulhi(slo * MU, kb::P));
+    const uint32_t sigma = umin(r, r + kb::P);
+    const uint32_t sigma_p = sigma + kb::P;
+    const uint32_t q0 = kb::mulhi(s[0] * MU, kb::P);
+    const uint32_t y0 = add_m<ALU>(sigma, add_m<ALU>(q0, q0));
+    s[1] = subw<ALU>(sigma_p, kb::mulhi(s[1] * MU, kb::P));
+#pragma unroll
+    for (int i = 2; i < 16; i++) {
+        const int k = (i == 15) ? 15 : (i - 1);
+        const uint32_t tlo = s[i] << k, thi = s[i] >> (32 - k);
+        s[i] = subw<ALU>(sigma_p + thi, kb::mulhi(tlo * MU, kb::P));
+    }
+    s[0] = y0;
+}
+
+template <int MODE, int UF = 2, int UP = 4>
+KB_HD void permute_m(uint32_t (&s)[16]) {
+    constexpr bool EA = (MODE & M_EXT_ALU) != 0, IA = (MODE & M_INT_ALU) != 0;
+    if (EA) ext_layer_m<true>(s); else ext_layer(s);
+#pragma unroll UF
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = sbox_m<MODE>(s[i], P2_RC.ext[r * 16 + i]);
+        if (EA) ext_layer_m<true>(s); else ext_layer(s);
+    }
+#pragma unroll UP
+    for (int r = 0; r < 20; r++) {
+        s[0] = sbox_m<MODE>(s[0], P2_RC.inr[r]);
+        if (IA) int_layer_m<true>(s); else int_layer_lazy(s);
+    }
+#pragma unroll
+    for (int i = 1; i < 16; i++) { uint32_t v = s[i]; v = umin(v, v - kb::P); s[i] = umin(v, v - kb::P); }
+#pragma unroll UF
+    for (int r = 4; r < 8; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = sbox_m<MODE>(s[i], P2_RC.ext[r * 16 + i]);
+        if (EA) ext_layer_m<true>(s); else ext_layer(s);
+    }
+}
+
+// the permutation every kernel of the library calls
+KB_HD void permute(uint32_t (&s)[16]) {
+    if (P2_DEFAULT_MODE == 0) permute_r1(s); else permute_m<P2_DEFAULT_MODE>(s);
 }
 
 // compress(L, R) = permute(L || R)[0..8]

@@ -3,6 +3,7 @@ kb31.cuh / poseidon2.cuh code the kernels run, checked against the oracle on the
 import ctypes as C
 
 import numpy as np
+import pytest
 
 from tests import oracle_lib as O
 
@@ -30,6 +31,17 @@ def test_device_poseidon2_source_on_host_matches_oracle():
     _L().sp1b200_hostcheck_permute(got.ctypes.data_as(O.u32p), C.c_uint64(got.shape[0]))
     assert (got == exp).all()
     assert (got < O.P).all()   # canonical outputs
+
+
+@pytest.mark.parametrize("mode", [-1] + list(range(16)))
+def test_every_permutation_mode_on_host_matches_oracle(mode):
+    """permute_m<MODE> (s-box reduction form, pipe placement of the additions) computes the same words as the oracle; -1 = the round-1 code"""
+    rng = np.random.default_rng(50 + mode)
+    st = _edge_states(rng, 300)
+    exp = np.stack([O.permute(s) for s in st])
+    got = st.copy()
+    assert _L().sp1b200_hostcheck_permute_mode(got.ctypes.data_as(O.u32p), C.c_uint64(got.shape[0]), C.c_int(mode)) == 1
+    assert (got == exp).all() and (got < O.P).all()
 
 
 def test_device_field_and_ext_sources_on_host():

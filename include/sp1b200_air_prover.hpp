@@ -74,7 +74,7 @@ class AirProver {
   public:
     // chips in name order; machine_blob = the constraint bytecode + interactions of every chip (sp1b200_machine_create)
     AirProver(int device, const sp1b200_params& params, std::vector<Chip> chips, const std::vector<uint32_t>& machine_blob)
-        : chips_(std::move(chips)) {
+        : params_(params), chips_(std::move(chips)) {
         check(sp1b200_ctx_create(device, &params, &ctx_));
         sp1b200_err e = sp1b200_machine_create(ctx_, machine_blob.data(), machine_blob.size(), &machine_);
         if (e) { std::string m = e; sp1b200_ctx_destroy(ctx_); throw Error(m.c_str()); }
@@ -174,10 +174,26 @@ class AirProver {
         return {std::move(pk), std::vector<uint32_t>(proof_buf_.begin(), proof_buf_.begin() + n)};
     }
 
+    // bincode(ShardProof) of a proof returned by prove_shard_with_pk / setup_and_prove_shard: the bytes the reference's workers, recursion
+    // tree and verifier exchange (crates/hypercube/src/verifier/proof.rs:47-61; sp1b200_shard_proof_to_bincode)
+    std::vector<uint8_t> to_bincode(const std::vector<uint32_t>& proof_words, const std::vector<uint64_t>& heights) const {
+        if (heights.size() != chips_.size()) throw Error("to_bincode: one height per chip expected");
+        std::vector<const char*> names; std::vector<uint32_t> mw, pw;
+        for (const auto& c : chips_) { names.push_back(c.name.c_str()); mw.push_back(c.main_width); pw.push_back(c.preprocessed_width); }
+        uint64_t n = 0;
+        check(sp1b200_shard_proof_to_bincode(&params_, (uint32_t)chips_.size(), names.data(), heights.data(), mw.data(), pw.data(), proof_words.data(),
+                                             proof_words.size(), nullptr, 0, &n));
+        std::vector<uint8_t> out(n);
+        check(sp1b200_shard_proof_to_bincode(&params_, (uint32_t)chips_.size(), names.data(), heights.data(), mw.data(), pw.data(), proof_words.data(),
+                                             proof_words.size(), out.data(), out.size(), &n));
+        return out;
+    }
+
     sp1b200_ctx* context() const { return ctx_; }
 
   private:
     static constexpr uint64_t kCapWords = 1ull << 24;
+    sp1b200_params params_;
     sp1b200_ctx* ctx_ = nullptr;
     sp1b200_machine* machine_ = nullptr;
     std::vector<Chip> chips_;

@@ -166,11 +166,15 @@ KB_HD void permute_r1(uint32_t (&s)[16]) {
 //              by construction (the all-ones operand comes from constant memory, so the compiler cannot fold the min away)
 //   M_INT_ALU  same for the subtractions  t - q  of the internal layer (VIADDMNMX with a negated operand)
 //   M_SB_HALF  s-box products by halves (IMAD + IMAD.HI) instead of IMAD.WIDE
-// tools/p2_bench.cu times the combinations (profiles/p2_bench_r02b.txt); P2_DEFAULT_MODE is the measured best.  Every mode computes the
-// same words: tests/test_hostcheck.py runs them on the host against the oracle, tools/p2_bench.cu and the GPU suite on the device.
+// tools/p2_modes.cu times the combinations (profiles/p2_modes_r02.txt); P2_DEFAULT_MODE is the measured best.  Every mode computes the
+// same words: tests/test_hostcheck.py runs them on the host against the oracle, tools/p2_modes.cu and the GPU suite on the device.
 enum : int { M_SB_SUB = 1, M_EXT_ALU = 2, M_INT_ALU = 4, M_SB_HALF = 8 };
+// measured on a B200 (tools/p2_modes.cu, profiles/p2_modes_r02.txt): round-1 code 4.62 Gperm/s; M_SB_SUB 5.00 (5.02 with the full-round loop
+// rolled); forcing additions onto the alu pipe loses (M_SB_SUB|M_EXT_ALU 4.82, |M_INT_ALU 4.94, all three 4.54): ncu shows the fmaheavy pipe
+// at 90 % in both the old and the new code, and the alu pipe saturating near 68 % once the additions are moved - ptxas' own split is close to the
+// balance point; M_SB_HALF loses as well (4.35).
 #ifndef P2_DEFAULT_MODE
-#define P2_DEFAULT_MODE 0
+#define P2_DEFAULT_MODE 1
 #endif
 static __constant__ uint32_t K_ONES = 0xffffffffu;
 
@@ -274,7 +278,7 @@ KB_HD void permute_m(uint32_t (&s)[16]) {
 
 // the permutation every kernel of the library calls
 KB_HD void permute(uint32_t (&s)[16]) {
-    if (P2_DEFAULT_MODE == 0) permute_r1(s); else permute_m<P2_DEFAULT_MODE>(s);
+    if (P2_DEFAULT_MODE == 0) permute_r1(s); else permute_m<P2_DEFAULT_MODE, 1, 4>(s);
 }
 
 // compress(L, R) = permute(L || R)[0..8]

@@ -624,10 +624,11 @@ def main():
         "roofline": {"kernel": "leaf_hash_kernel (Poseidon2 sponge over the 2^23 codeword rows of the main commit; largest share of the step)",
                      "bound": "hbm", "achieved": leaf_gbs, "peak": hbm, "unit": "GB/s", "frac": leaf_gbs / hbm,
                      "traffic": LEAF_TRAFFIC_BYTES_PER_LAUNCH, "algorithmic_bytes_per_launch": leaf_bytes, "peak_source": peak_src,
-                     "limiter": "integer issue, not HBM: 12 Poseidon2 permutations per 412-byte row; the permutation costs ~63 SM-clocks "
-                                "per lane under the measured per-instruction issue rates (IMAD.HI 43/clk/SM dominates), "
-                                "i.e. ~4.4 Gperm/s per GPU at 1.9 GHz; see DESIGN.md section 3",
-                     "gperm_per_s": leaf_perms / (leaf_ms / 1e3) / 1e9, "issue_model_gperm_per_s": 4.43,
+                     "limiter": "the fmaheavy integer-multiply pipe, not HBM: 12 Poseidon2 permutations per 412-byte row; ncu shows "
+                                "sm__pipe_fmaheavy_cycles_active 90 %, fmalite 0 %, alu 61 % (profiles/ncu_p2_pipes_r02.txt): every IMAD* "
+                                "instruction of the permutation (3 434 pipe slots per permutation after the round-2 s-box change, 3 724 before) "
+                                "runs on that one pipe; register-resident permutations reach 5.02 Gperm/s (tools/p2_modes.cu), see DESIGN.md section 3.1",
+                     "gperm_per_s": leaf_perms / (leaf_ms / 1e3) / 1e9, "register_resident_gperm_per_s": 5.02,
                      "note": "algorithmic bytes = (4 B x stacked columns + 32 B digest) x 2^23 rows per launch; CUDA events on the library "
                              "stream (phase merkle.leaf_hash); traffic = dram read+write of the same launch under ncu --set full (profiles/)"},
         "roofline_rs_encode": {"kernel": "rs_encode (rs_step_a_fast<10> + rs_step_b_2048), all stacked columns of the main commit",

@@ -25,6 +25,7 @@ int sp1b200_hostcheck_permute_mode(uint32_t* states, uint64_t n, int mode) {
 #define P2_CASE(M) case M: p2::permute_m<M>(s); break;
             P2_CASE(0) P2_CASE(1) P2_CASE(2) P2_CASE(3) P2_CASE(4) P2_CASE(5) P2_CASE(6) P2_CASE(7)
             P2_CASE(8) P2_CASE(9) P2_CASE(10) P2_CASE(11) P2_CASE(12) P2_CASE(13) P2_CASE(14) P2_CASE(15)
+            P2_CASE(19) P2_CASE(21) P2_CASE(23)
 #undef P2_CASE
             case -1: p2::permute_r1(s); break;
             default: return 0;

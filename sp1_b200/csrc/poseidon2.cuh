@@ -168,7 +168,9 @@ KB_HD void permute_r1(uint32_t (&s)[16]) {
 //   M_SB_HALF  s-box products by halves (IMAD + IMAD.HI) instead of IMAD.WIDE
 // tools/p2_modes.cu times the combinations (profiles/p2_modes_r02.txt); P2_DEFAULT_MODE is the measured best.  Every mode computes the
 // same words: tests/test_hostcheck.py runs them on the host against the oracle, tools/p2_modes.cu and the GPU suite on the device.
-enum : int { M_SB_SUB = 1, M_EXT_ALU = 2, M_INT_ALU = 4, M_SB_HALF = 8 };
+//   M_ADD3     the forcing primitive of M_EXT_ALU / M_INT_ALU is the three-input IADD3  a + b + 0  (opaque zero from constant memory) instead
+//              of VIADDMNMX: an IADD3 with three live operands cannot be turned into IMAD.IADD
+enum : int { M_SB_SUB = 1, M_EXT_ALU = 2, M_INT_ALU = 4, M_SB_HALF = 8, M_ADD3 = 16 };
 // measured on a B200 (tools/p2_modes.cu, profiles/p2_modes_r02.txt): round-1 code 4.62 Gperm/s; M_SB_SUB 5.00 (5.02 with the full-round loop
 // rolled); forcing additions onto the alu pipe loses (M_SB_SUB|M_EXT_ALU 4.82, |M_INT_ALU 4.94, all three 4.54): ncu shows the fmaheavy pipe
 // at 90 % in both the old and the new code, and the alu pipe saturating near 68 % once the additions are moved - ptxas' own split is close to the
@@ -177,22 +179,26 @@ enum : int { M_SB_SUB = 1, M_EXT_ALU = 2, M_INT_ALU = 4, M_SB_HALF = 8 };
 #define P2_DEFAULT_MODE 1
 #endif
 static __constant__ uint32_t K_ONES = 0xffffffffu;
+static __constant__ uint32_t K_ZERO = 0u;
 
-template <bool ALU> KB_HD uint32_t addw(uint32_t a, uint32_t b) {   // a + b mod 2^32
+// ALU: 0 = the compiler's choice, 1 = VIADDMNMX(a + b, ones), 2 = IADD3(a, b, zero)
+template <int ALU> KB_HD uint32_t addw(uint32_t a, uint32_t b) {   // a + b mod 2^32
 #ifdef __CUDA_ARCH__
-    if (ALU) return __viaddmin_u32(a, b, K_ONES);
+    if (ALU == 1) return __viaddmin_u32(a, b, K_ONES);
+    if (ALU == 2) return a + b + K_ZERO;
 #endif
     return a + b;
 }
-template <bool ALU> KB_HD uint32_t subw(uint32_t a, uint32_t b) {   // a - b mod 2^32
+template <int ALU> KB_HD uint32_t subw(uint32_t a, uint32_t b) {   // a - b mod 2^32
 #ifdef __CUDA_ARCH__
-    if (ALU) return __viaddmin_u32(a, 0u - b, K_ONES);
+    if (ALU == 1) return __viaddmin_u32(a, 0u - b, K_ONES);
+    if (ALU == 2) return a - b + K_ZERO;
 #endif
     return a - b;
 }
-template <bool ALU> KB_HD uint32_t add_m(uint32_t a, uint32_t b) { const uint32_t t = addw<ALU>(a, b); return umin(t, t - kb::P); }
+template <int ALU> KB_HD uint32_t add_m(uint32_t a, uint32_t b) { const uint32_t t = addw<ALU>(a, b); return umin(t, t - kb::P); }
 
-template <bool ALU> KB_HD void mds4_m(uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
+template <int ALU> KB_HD void mds4_m(uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
     uint32_t t01 = add_m<ALU>(s0, s1), t23 = add_m<ALU>(s2, s3);
     uint32_t t0123 = add_m<ALU>(t01, t23);
     uint32_t t01123 = add_m<ALU>(t0123, s1);
@@ -203,7 +209,7 @@ template <bool ALU> KB_HD void mds4_m(uint32_t& s0, uint32_t& s1, uint32_t& s2, 
     uint32_t n2 = add_m<ALU>(t01233, t23);
     s0 = n0; s1 = n1; s2 = n2; s3 = n3;
 }
-template <bool ALU> KB_HD void ext_layer_m(uint32_t (&s)[16]) {
+template <int ALU> KB_HD void ext_layer_m(uint32_t (&s)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; i += 4) mds4_m<ALU>(s[i], s[i + 1], s[i + 2], s[i + 3]);
     uint32_t c0 = add_m<ALU>(add_m<ALU>(s[0], s[4]), add_m<ALU>(s[8], s[12]));
@@ -231,7 +237,7 @@ template <int MODE> KB_HD uint32_t sbox_m(uint32_t s, uint32_t rc) {
     return umin(r, r + kb::P);
 }
 
-template <bool ALU> KB_HD void int_layer_m(uint32_t (&s)[16]) {   // int_layer_lazy with the subtractions placed on the alu pipe
+template <int ALU> KB_HD void int_layer_m(uint32_t (&s)[16]) {   // int_layer_lazy with the subtractions placed on the alu pipe
     uint64_t sum = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) sum += s[i];
@@ -253,18 +259,18 @@ template <bool ALU> KB_HD void int_layer_m(uint32_t (&s)[16]) {   // int_layer_l
 
 template <int MODE, int UF = 2, int UP = 4>
 KB_HD void permute_m(uint32_t (&s)[16]) {
-    constexpr bool EA = (MODE & M_EXT_ALU) != 0, IA = (MODE & M_INT_ALU) != 0;
-    if (EA) ext_layer_m<true>(s); else ext_layer(s);
+    constexpr int F = (MODE & M_ADD3) ? 2 : 1, EA = (MODE & M_EXT_ALU) ? F : 0, IA = (MODE & M_INT_ALU) ? F : 0;
+    if (EA) ext_layer_m<EA>(s); else ext_layer(s);
 #pragma unroll UF
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < 16; i++) s[i] = sbox_m<MODE>(s[i], P2_RC.ext[r * 16 + i]);
-        if (EA) ext_layer_m<true>(s); else ext_layer(s);
+        if (EA) ext_layer_m<EA>(s); else ext_layer(s);
     }
 #pragma unroll UP
     for (int r = 0; r < 20; r++) {
         s[0] = sbox_m<MODE>(s[0], P2_RC.inr[r]);
-        if (IA) int_layer_m<true>(s); else int_layer_lazy(s);
+        if (IA) int_layer_m<IA>(s); else int_layer_lazy(s);
     }
 #pragma unroll
     for (int i = 1; i < 16; i++) { uint32_t v = s[i]; v = umin(v, v - kb::P); s[i] = umin(v, v - kb::P); }
@@ -272,7 +278,7 @@ KB_HD void permute_m(uint32_t (&s)[16]) {
     for (int r = 4; r < 8; r++) {
 #pragma unroll
         for (int i = 0; i < 16; i++) s[i] = sbox_m<MODE>(s[i], P2_RC.ext[r * 16 + i]);
-        if (EA) ext_layer_m<true>(s); else ext_layer(s);
+        if (EA) ext_layer_m<EA>(s); else ext_layer(s);
     }
 }
 

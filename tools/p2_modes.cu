@@ -1,7 +1,7 @@
 // Poseidon2 permutation: instruction-selection modes of p2::permute_m<MODE, UF, UP> (sp1_b200/csrc/poseidon2.cuh) on a B200, Gperm/s with
 // the state in registers; every variant is compared word for word with the round-1 code p2::permute_r1 (oracle-checked in the GPU suite).
 // MODE bits: 1 = subtractive s-box reduction, 2 = external-layer additions forced to the alu pipe, 4 = internal-layer subtractions forced
-// to the alu pipe, 8 = s-box products by halves.  UF / UP = unroll factors of the full / partial round loops.
+// to the alu pipe, 8 = s-box products by halves, 16 = force with IADD3(a, b, 0) instead of VIADDMNMX(a + b, ones).  UF / UP = unroll factors of the full / partial round loops.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -I../sp1_b200/csrc -o p2_modes p2_modes.cu
 #include <cstdio>
 #include <cstdint>
@@ -66,13 +66,14 @@ int main(int argc, char** argv) {
     if (argc > 2 && !strcmp(argv[1], "only")) {   // p2_modes only <mode>...  (profiling: a few launches of the named modes)
         for (int i = 2; i < argc; i++) switch (atoi(argv[i])) {
             case -1: run<-1>(d, sms); break; case 0: run<0>(d, sms); break; case 1: run<1>(d, sms); break; case 3: run<3>(d, sms); break;
-            case 5: run<5>(d, sms); break; case 7: run<7>(d, sms); break; default: printf("mode %s not compiled in\n", argv[i]);
+            case 5: run<5>(d, sms); break; case 7: run<7>(d, sms); break; case 23: run<23>(d, sms); break; case 19: run<19>(d, sms); break; default: printf("mode %s not compiled in\n", argv[i]);
         }
         return 0;
     }
     run<-1>(d, sms);
     run<0>(d, sms); run<1>(d, sms); run<2>(d, sms); run<3>(d, sms); run<4>(d, sms); run<5>(d, sms); run<6>(d, sms); run<7>(d, sms);
     run<8>(d, sms); run<9>(d, sms); run<11>(d, sms); run<13>(d, sms); run<15>(d, sms);
+    run<19>(d, sms); run<21>(d, sms); run<23>(d, sms); run<19, 1, 4>(d, sms); run<21, 1, 4>(d, sms); run<23, 1, 4>(d, sms); run<23, 2, 5>(d, sms); run<23, 1, 2>(d, sms);
     // loop shapes for the subtractive s-box family (the code is ~11 % shorter than round 1's, the instruction-cache optimum may move)
     run<1, 1, 4>(d, sms); run<1, 4, 4>(d, sms); run<1, 2, 5>(d, sms); run<1, 2, 10>(d, sms); run<1, 4, 10>(d, sms); run<1, 4, 20>(d, sms); run<1, 1, 2>(d, sms);
     run<3, 1, 4>(d, sms); run<3, 4, 4>(d, sms); run<3, 2, 5>(d, sms); run<3, 2, 10>(d, sms); run<3, 4, 10>(d, sms);

@@ -32,26 +32,12 @@ KB_HD uint32_t mulhi(uint32_t a, uint32_t b) {
 #endif
 }
 
-// KB_ALU_ADD (per translation unit, csrc/Makefile): the first instruction of every modular addition / subtraction / reduction
-// difference is written as the THREE-input add  a + b + 0  with the zero read from constant memory.  ptxas balances plain two-input
-// additions between IADD3 (alu pipe) and IMAD.IADD (multiplier pipe); on a B200 every IMAD* runs on the fmaheavy pipe, which is the one
-// the field kernels saturate (profiles/ncu_p2_pipes_r02.txt), so the additions belong on the alu pipe.  A three-input IADD3 cannot be
-// expressed as IMAD.IADD.  Same values either way.
-#if defined(KB_ALU_ADD) && defined(__CUDACC__)
-static __constant__ uint32_t KB_ZERO_WORD = 0u;
-#endif
-#if defined(KB_ALU_ADD) && defined(__CUDA_ARCH__)
-#define KB_Z kb::KB_ZERO_WORD
-#else
-#define KB_Z 0u
-#endif
-
 KB_HD uint32_t add(uint32_t a, uint32_t b) {
-    uint32_t s = a + b + KB_Z;  // < 2p < 2^32
+    uint32_t s = a + b;  // < 2p < 2^32
     return umin(s, s - P);
 }
 KB_HD uint32_t sub(uint32_t a, uint32_t b) {
-    uint32_t d = a - b + KB_Z;
+    uint32_t d = a - b;
     return umin(d, d + P);
 }
 KB_HD uint32_t neg(uint32_t a) { return a ? P - a : 0u; }
@@ -63,7 +49,7 @@ KB_HD uint32_t dbl(uint32_t a) { return add(a, a); }
 constexpr uint32_t MU = 0x81000001u;  // +p^-1 mod 2^32
 KB_HD uint32_t monty_reduce(uint64_t x) {
     uint32_t q = mulhi((uint32_t)x * MU, P);
-    uint32_t r = (uint32_t)(x >> 32) - q + KB_Z;  // in (-p, p)
+    uint32_t r = (uint32_t)(x >> 32) - q;  // in (-p, p)
     return umin(r, r + P);
 }
 // same for x < 2 p * 2^32 (e.g. a sum of up to four products of canonical values: 4 (p-1)^2 < 2 p 2^32)
@@ -71,7 +57,7 @@ KB_HD uint32_t monty_reduce2(uint64_t x) {
     uint32_t hi = (uint32_t)(x >> 32);
     hi = umin(hi, hi - P);
     uint32_t q = mulhi((uint32_t)x * MU, P);
-    uint32_t r = hi - q + KB_Z;
+    uint32_t r = hi - q;
     return umin(r, r + P);
 }
 // additive form, result only partially reduced: [0, 2p) when x < 2^32 * p

@@ -9,8 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# SP1B200_LIB selects another build of the same library (development: `make -C sp1_b200/csrc ALT=1` -> libsp1b200_alu.so)
-SO_PATH = os.environ.get("SP1B200_LIB") or os.path.join(HERE, "libsp1b200.so")
+SO_PATH = os.path.join(HERE, "libsp1b200.so")
 
 u32p = C.POINTER(C.c_uint32)
 

@@ -35,6 +35,16 @@ def _run(spec, log_stack, mlr, seed, nq=8, pow_bits=4, batch_bits=2, gkr_bits=3)
     bad = np.nonzero(words != owords)[0]
     assert bad.size == 0, f"first differing words {bad[:8]} of {words.size} (sections {owords[:6]})"
     assert (st == och.st).all()
+    # the wire format of the GPU proof: bincode(ShardProof) decoded by the independent reader of the Rust struct definitions gives back
+    # the same words, names and heights (tests/test_wire.py covers the format itself on the CPU)
+    from sp1_b200 import lib as PL
+    from tests import bincode_ref as BR
+    from tests.test_wire import _widths
+    w = _widths(blob)
+    prm = dict(log_stacking_height=log_stack, max_log_row_count=mlr, num_queries=nq, pow_bits=pow_bits, batch_pow_bits=batch_bits, gkr_pow_bits=gkr_bits)
+    data = PL.shard_proof_to_bincode(words, names, heights, [a for a, _ in w], [b for _, b in w], **prm)
+    flat, dn, dh = BR.flatten(BR.decode_shard_proof(data))
+    assert dn == names and dh == list(heights) and (np.array(flat, dtype=np.uint64) == words).all()
     if prep_round is not None:
         lib.jagged_round_free(prep_round)
     lib.machine_free(mach)

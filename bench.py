@@ -4,7 +4,7 @@
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
   python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
 
-A "step" proves one batch of `--inflight` synthetic shards per GPU (default 5 for S2, each on its own library context + CUDA stream +
+A "step" proves one batch of `--inflight` synthetic shards per GPU (default 7 for S2, each on its own library context + CUDA stream +
 host transcript thread, so that the latency-bound sumcheck tails of one shard overlap the NTT / Poseidon2 kernels of another);
 a shard = workload S2 by default (~1.9e8 trace cells = 2^22 cycles at 45 cells/cycle): main-trace jagged commit (RS-encode NTT +
 Poseidon2 Merkle) followed by the phases listed in config.phases.  Per-phase times and the roofline lines are taken from a
@@ -32,7 +32,7 @@ PHASES_DONE = ["commit(main): rs_encode + poseidon2 merkle", "logup-gkr: grind(1
                "zerocheck: constraint bytecode interpreter, 22 rounds over all chips",
                "jagged open: hadamard sumcheck + branching-program sumcheck",
                "stacked/basefold open: batch + 21 fold rounds + 2 grinds + 124 queries"]
-LEAF_TRAFFIC_BYTES_PER_LAUNCH = 3.193006e9 + 0.266801e9  # dram read + write of the S2 launch, profiles/ncu_big_kernels_r01_S2.txt
+LEAF_TRAFFIC_BYTES_PER_LAUNCH = 3.191007e9 + 0.265294e9  # dram read + write of the 95-column S2c launch, profiles/ncu_leaf_hash_r02.txt (ncu --set full)
 PHASES_MISSING = []  # the step is the whole prove_shard_with_data body (shard.rs:650-792) on synthetic AIRs
 
 
@@ -194,7 +194,7 @@ def run_reference(args):
 def default_inflight(args):
     """shards proven concurrently per GPU: as many as the device memory comfortably holds (measured: 13.7 GB per calibrated 2^22-cycle
     context, 26-32 GB per full shard; throughput saturates at 5 / 4 contexts: S3c 73.4 M cycles/s at three, 78.1 M at four in flight)"""
-    return args.inflight if args.inflight > 0 else {"S1": 5, "S2": 5, "S1c": 5, "S2c": 5, "R1": 5, "tiny": 4, "tinyc": 4, "tinyr": 4}.get(args.workload, 4)
+    return args.inflight if args.inflight > 0 else {"S1": 5, "S2": 7, "S1c": 5, "S2c": 7, "R1": 5, "tiny": 4, "tinyc": 4, "tinyr": 4}.get(args.workload, 4)
 
 
 def workload_config(workload, cells, cycles, n_chips, inflight):

@@ -4,7 +4,7 @@
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
   python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
 
-A "step" proves one batch of `--inflight` synthetic shards per GPU (default 7 for S2, each on its own library context + CUDA stream +
+A "step" proves one batch of `--inflight` synthetic shards per GPU (default 6 for S2, each on its own library context + CUDA stream +
 host transcript thread, so that the latency-bound sumcheck tails of one shard overlap the NTT / Poseidon2 kernels of another);
 a shard = workload S2 by default (~1.9e8 trace cells = 2^22 cycles at 45 cells/cycle): main-trace jagged commit (RS-encode NTT +
 Poseidon2 Merkle) followed by the phases listed in config.phases.  Per-phase times and the roofline lines are taken from a
@@ -194,7 +194,7 @@ def run_reference(args):
 def default_inflight(args):
     """shards proven concurrently per GPU: as many as the device memory comfortably holds (measured: 13.7 GB per calibrated 2^22-cycle
     context, 26-32 GB per full shard; throughput saturates at 5 / 4 contexts: S3c 73.4 M cycles/s at three, 78.1 M at four in flight)"""
-    return args.inflight if args.inflight > 0 else {"S1": 5, "S2": 7, "S1c": 5, "S2c": 7, "R1": 5, "tiny": 4, "tinyc": 4, "tinyr": 4}.get(args.workload, 4)
+    return args.inflight if args.inflight > 0 else {"S1": 5, "S2": 6, "S1c": 5, "S2c": 6, "R1": 5, "tiny": 4, "tinyc": 4, "tinyr": 4}.get(args.workload, 4)
 
 
 def workload_config(workload, cells, cycles, n_chips, inflight):

@@ -124,3 +124,61 @@ def test_bincode_rejects_malformed_input():
         return
     prm = {k: v for k, v in p["params"].items() if k not in ("log_stacking_height", "max_log_row_count")}
     assert O.verify_shard(p["blob"], heights, p["names"], log_stack, mlr, p["start"].clone(), p["prep_commit"], words, **prm) != 0
+
+
+def test_bincode_reader_survives_random_corruption():
+    """memory safety of the byte reader: random byte flips, length-prefix overwrites and truncations must end in an error message or a
+    parsed proof - never in a crash or an over-read (every length prefix is checked against the bytes that remain)"""
+    spec, log_stack, mlr = CASES[2]
+    p = _proof(spec, log_stack, mlr)
+    args = (p["names"], p["main_w"], p["prep_w"])
+    data = PL.shard_proof_to_bincode(p["words"], p["names"], p["heights"], p["main_w"], p["prep_w"], **p["params"])
+    rng = np.random.default_rng(2024)
+    outcomes = {"error": 0, "parsed": 0}
+    for trial in range(400):
+        b = bytearray(data)
+        kind = trial % 4
+        if kind == 0:                                   # a few random byte flips
+            for pos in rng.integers(0, len(b), size=int(rng.integers(1, 6))):
+                b[pos] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:                                 # overwrite 8 bytes somewhere with a huge / random u64 (hits length prefixes often)
+            pos = int(rng.integers(0, len(b) - 8))
+            b[pos:pos + 8] = struct.pack("<Q", int(rng.integers(0, 1 << 62)) if trial % 8 == 1 else (1 << 63) + 5)
+        elif kind == 2:                                 # truncate
+            b = b[:int(rng.integers(0, len(b)))]
+        else:                                           # splice a random window out
+            a = int(rng.integers(0, len(b) - 16)); b = b[:a] + b[a + int(rng.integers(1, 16)):]
+        try:
+            words, heights = PL.shard_proof_from_bincode(bytes(b), *args, **p["params"])
+            assert words[0] == 5 and len(heights) == len(p["names"])
+            outcomes["parsed"] += 1
+        except PL.Sp1B200Error as e:
+            assert str(e).startswith("shard_proof_from_bincode:")
+            outcomes["error"] += 1
+    assert outcomes["error"] > 200 and outcomes["parsed"] + outcomes["error"] == 400, outcomes
+
+
+def test_bincode_reader_under_sanitizers(tmp_path):
+    """the wire code (host-only) compiled as plain C++ with -fsanitize=address,undefined and driven by tools/fuzz_wire.cpp over mutated
+    proofs in exact-size heap buffers: any over-read, overflow or UB aborts the run"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(HERE)
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "fuzz_wire")
+    cc = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-x", "c++",
+                         f"-I{root}/include", f"-I{root}/sp1_b200/csrc", "-I/usr/local/cuda/include", f"{root}/tools/fuzz_wire.cpp",
+                         f"{root}/sp1_b200/csrc/wire.cu", "-o", exe], capture_output=True, text=True)
+    if cc.returncode != 0:
+        pytest.skip("sanitizer build unavailable here: " + cc.stderr[-300:])
+    spec, log_stack, mlr = CASES[2]
+    p = _proof(spec, log_stack, mlr)
+    data = PL.shard_proof_to_bincode(p["words"], p["names"], p["heights"], p["main_w"], p["prep_w"], **p["params"])
+    f = tmp_path / "proof.bin"
+    f.write_bytes(data)
+    widths = [str(x) for pair in zip(p["main_w"], p["prep_w"]) for x in pair]
+    run = subprocess.run([exe, str(f), str(log_stack), str(mlr), str(len(p["names"]))] + widths, capture_output=True, text=True,
+                         env=dict(os.environ, FUZZ_TRIALS="6000"), timeout=300)
+    assert run.returncode == 0, run.stderr[-2000:]
+    assert run.stdout.startswith("parsed ")

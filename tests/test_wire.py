@@ -182,3 +182,17 @@ def test_bincode_reader_under_sanitizers(tmp_path):
                          env=dict(os.environ, FUZZ_TRIALS="6000"), timeout=300)
     assert run.returncode == 0, run.stderr[-2000:]
     assert run.stdout.startswith("parsed ")
+
+
+def test_bincode_golden_fixtures():
+    """committed SHA-256 of the wire bytes of the golden proofs (tests/golden/shard_proofs_bincode.json, tools/gen_golden_proofs.py --bincode):
+    pins the byte layout against accidental change; the proof words behind them are the ones tests/golden/shard_proofs.json pins"""
+    import hashlib
+    from tools import gen_golden_proofs as GG
+    gold = {c["name"]: c for c in json.load(open(os.path.join(HERE, "golden", "shard_proofs_bincode.json")))["cases"]}
+    words_gold = {c["name"]: c for c in json.load(open(os.path.join(HERE, "golden", "shard_proofs.json")))["cases"]}
+    for case in GG.CASES:
+        got = GG.bincode_case(*case)
+        g = gold[case[0]]
+        assert got["words_sha256"] == words_gold[case[0]]["sha256"] == g["words_sha256"]
+        assert got["bincode_bytes"] == g["bincode_bytes"] and got["bincode_sha256"] == g["bincode_sha256"], case[0]

@@ -93,9 +93,35 @@ def full_size(workloads):
     print("wrote", path, [c["sha256"][:12] for c in out["cases"]])
 
 
+def bincode_case(name, spec, log_stack, mlr, seed, nq, pw, bpw, gpw):
+    """the wire bytes of the same seeded proof: bincode(ShardProof) written by the product's host-only converter"""
+    from sp1_b200 import lib as PL
+    from tests.test_wire import _widths
+    rng = np.random.default_rng(seed)
+    blob, heights, mains, preps, pv = _synth_machine_gkr(rng, spec)
+    names = [f"Chip{i:02d}" for i in range(len(heights))]
+    ch = O.Challenger()
+    ch.observe(O.rand_field(rng, 9))
+    _, words = O.prove_shard_verify(blob, heights, mains, preps, names, pv, log_stack, mlr, ch, num_queries=nq, pow_bits=pw, batch_pow_bits=bpw,
+                                    gkr_pow_bits=gpw)
+    w = _widths(blob)
+    data = PL.shard_proof_to_bincode(words, names, heights, [a for a, _ in w], [b for _, b in w], log_stacking_height=log_stack,
+                                     max_log_row_count=mlr, num_queries=nq, pow_bits=pw, batch_pow_bits=bpw, gkr_pow_bits=gpw)
+    return {"name": name, "words_sha256": hashlib.sha256(words.astype("<u4").tobytes()).hexdigest(), "bincode_bytes": len(data),
+            "bincode_sha256": hashlib.sha256(data).hexdigest(), "head_hex": data[:64].hex()}
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--full":
         return full_size(sys.argv[2:] or ["S1"])
+    if len(sys.argv) > 1 and sys.argv[1] == "--bincode":
+        out = {"generator": "tools/gen_golden_proofs.py --bincode (the proofs of shard_proofs.json as bincode(ShardProof), csrc/wire.cu)",
+               "cases": [bincode_case(*c) for c in CASES]}
+        path = os.path.join(ROOT, "tests", "golden", "shard_proofs_bincode.json")
+        with open(path, "w") as f:
+            json.dump(out, f, indent=1)
+        print("wrote", path, [c["bincode_sha256"][:12] for c in out["cases"]])
+        return
     out = {"generator": "tools/gen_golden_proofs.py (oracle/liboracle.so; minimum-witness grinding)",
            "format": "proof words = [n_sections][lengths] then main commitment | LogUp-GKR | zerocheck + opened values | evaluation proof | "
                      "public values; u32 little-endian for the hash",

@@ -192,8 +192,9 @@ def run_reference(args):
 
 
 def default_inflight(args):
-    """shards proven concurrently per GPU: as many as the device memory comfortably holds (measured: 13.7 GB per calibrated 2^22-cycle
-    context, 26-32 GB per full shard; throughput saturates at 5 / 4 contexts: S3c 73.4 M cycles/s at three, 78.1 M at four in flight)"""
+    """shards proven concurrently per GPU (measured: 13.7 GB per calibrated 2^22-cycle context, 26-32 GB per full shard; S2c: 73.5 / 74.4 /
+    75.5 / 75.2 M cycles/s at five / six / seven / eight in flight, six keeps 8 ranks x 6 host transcript threads within a 64-core host;
+    S3c 73.4 M cycles/s at three, 78.1 M at four in flight)"""
     return args.inflight if args.inflight > 0 else {"S1": 5, "S2": 6, "S1c": 5, "S2c": 6, "R1": 5, "tiny": 4, "tinyc": 4, "tinyr": 4}.get(args.workload, 4)
 
 

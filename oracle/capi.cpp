@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see field.hpp header).  PARITY UNPINNED BY STORED FIXTURES.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see field.hpp header: primitives pinned to the reference's own CUDA kernels, protocol glue unpinned).
 // C entry points for tests/ (ctypes), __graft_entry__.smoke() and bench.py's cpu_baseline leg.
 // All field elements cross this boundary as u32 Montgomery words (the reference's in-memory form).
 #include "gkr.hpp"

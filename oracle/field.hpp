@@ -1,8 +1,12 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Nothing under sp1_b200/ may include, link or call this.
-// PARITY UNPINNED BY STORED FIXTURES: the reference holds no golden vectors / KATs for this path
-// (SURVEY.md §4, §8c); this restatement is pinned only by (i) the constant tables extracted from the
-// reference (tests/golden/ref_constants.json), (ii) prover -> restated-verifier round trips and
-// (iii) algebraic identities (naive DFT, field axioms).
+// PARITY: the reference holds no golden vectors / KATs for this path.  What pins this restatement:
+// (i) the constant tables extracted from the reference (tests/golden/ref_constants.json); (ii) since round 2 the PRIMITIVES - field and
+// extension arithmetic, Poseidon2 permute / hash / compress, the Merkle tree, the coset DFT, the device challenger and grinding, the BaseFold
+// batch / fold kernels, the eq-table order, the LogUp first layer and the zerocheck bytecode interpreter - run bit-identical to the
+// reference's own CUDA kernels compiled unmodified as oracle/_ref (tests/test_gpu_ref_kernels.py); (iii) prover -> restated-verifier round
+// trips and algebraic identities (naive DFT, field axioms).  STILL UNPINNED BY REFERENCE-HELD VECTORS: the protocol glue that lives only in
+// the reference's Rust (transcript order of prove_shard_with_data, round-polynomial forms, padding / geq corrections, the branching program,
+// the BaseFold query layout) - cargo is absent from this image; DESIGN.md section 4 lists both sides.
 //
 // KoalaBear field p = 2^31 - 2^24 + 1 in Montgomery form R = 2^32, and its degree-4 extension
 // F[x]/(x^4 - 3).  Restates
